@@ -1,0 +1,177 @@
+/* picklebot_b200 -- C ABI of the B200 (sm_100a) kernels behind Picklebot's 3D mobile CNN hot path.
+ *
+ * The reference (hbfreed/Picklebot) has no FFI of its own: every op of the hot path is a torch.nn
+ * module call (mobilenet.py, movinet.py).  Each entry point below therefore cites the reference
+ * *operator* it replaces (file:line in /root/reference).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers.
+ *   - Activations are NDHWC (channels-last-3d): row-major X[M][C], M = B*T*H*W, C % 8 == 0, base
+ *     pointers 16-byte aligned.  `dtype` selects the activation storage type (PB_F32 / PB_BF16);
+ *     parameters, statistics and parameter gradients are always fp32 (fp64 for raw sums).
+ *   - The caller owns every buffer, including workspaces; the library allocates nothing on the
+ *     device and keeps no pointers after a call returns.
+ *   - Every call only enqueues work on `stream` (a cudaStream_t); no host synchronisation.
+ *   - Return value: PB_OK or an error code; pb_last_error_string() describes the last failure on
+ *     the calling thread.  Unsupported shapes are errors -- there is no CPU or library fallback.
+ *   - Re-entrant: forward is typically called from the Python main thread and backward from the
+ *     autograd engine's device thread.
+ */
+#ifndef PICKLEBOT_B200_H
+#define PICKLEBOT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_ABI_VERSION 1
+
+enum { PB_OK = 0, PB_ERR_BAD_ARG = 1, PB_ERR_UNSUPPORTED = 2, PB_ERR_CUDA = 3 };
+enum { PB_F32 = 0, PB_BF16 = 1, PB_U8 = 2,
+       PB_F32_RBF16 = 16 /* pb_cast_matrix only: fp32 storage, values rounded through bf16 */ };
+enum { PB_ACT_NONE = 0, PB_ACT_RELU = 1, PB_ACT_HSWISH = 2, PB_ACT_LRELU = 3, PB_ACT_HSIGMOID = 4 };
+
+typedef void* pb_stream_t; /* cudaStream_t */
+
+int         pb_abi_version(void);
+const char* pb_last_error_string(void);
+long long   pb_launch_count(void);      /* kernels launched by this library since load (all threads) */
+int         pb_device_check(void);      /* PB_OK iff the current device is sm_100 (B200) */
+
+/* ------------------------------------------------------------------------------------------------
+ * Depthwise Conv3d, groups == C.  Replaces Bottleneck3D.depthwise_conv (mobilenet.py:67-75,86: kernel
+ * (1,k,k) with SCALAR stride/padding, so time is padded and strided too) and MoviNetBottleneck.conv
+ * (movinet.py:52-61,71: (kT,kH,kW), stride (1,s,s)), plus their autograd (train.py:269).
+ *   x  [B][T][H][W][C], y/dy [B][To][Ho][Wo][C]; w_tc: fp32 weights repacked tap-major [kT*kH*kW][C]
+ *   (pb_cast_matrix(..., transpose=1) of the (C,1,kT,kH,kW) parameter viewed as [C][taps]).  wgrad overwrites dw_tc (same layout).
+ * ---------------------------------------------------------------------------------------------- */
+int pb_dwconv3d_fwd(const void* x, const float* w_tc, void* y, int dtype,
+                    int B, int C, int T, int H, int W, int kT, int kH, int kW,
+                    int sT, int sH, int sW, int pT, int pH, int pW, int To, int Ho, int Wo,
+                    pb_stream_t stream);
+int pb_dwconv3d_dgrad(const void* dy, const float* w_tc, void* dx, int dtype,
+                      int B, int C, int T, int H, int W, int kT, int kH, int kW,
+                      int sT, int sH, int sW, int pT, int pH, int pW, int To, int Ho, int Wo,
+                      pb_stream_t stream);
+int pb_dwconv3d_wgrad(const void* x, const void* dy, float* dw_tc, int dtype,
+                      int B, int C, int T, int H, int W, int kT, int kH, int kW,
+                      int sT, int sH, int sW, int pT, int pH, int pW, int To, int Ho, int Wo,
+                      pb_stream_t stream);
+
+/* Causal streaming variant (CausalConv3d semantics, movinet.py:23-39, applied to MoViNet's depthwise
+ * convs): time is left-padded by kT-1 frames taken from `stream_buf` [B][kT-1][H][W][C] (the tail of
+ * the previous chunk; zeros for the first chunk), temporal stride 1, To == T.  After the conv the last
+ * kT-1 input frames are written back to `stream_buf_out` (may alias stream_buf only if kT-1 <= T). */
+int pb_stream_dwconv3d_fwd(const void* x, const void* stream_buf, const float* w_tc, void* y,
+                           void* stream_buf_out, int dtype,
+                           int B, int C, int T, int H, int W, int kT, int kH, int kW,
+                           int sH, int sW, int pH, int pW, int Ho, int Wo, pb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pointwise (1x1x1) convolutions and fully connected layers as GEMMs.  Replaces
+ * Bottleneck3D.pointwise_conv1/2 (mobilenet.py:64,79,85,89), MoviNetBottleneck.expand/project
+ * (movinet.py:47,63-64), block6 / block4 convs (mobilenet.py:179,245), `conv` (movinet.py:140) and the
+ * classifier layers (mobilenet.py:185-190, movinet.py:146-154).
+ *
+ *   C[b][r][n] = ( sum_k A[b][r][k] * ascale[b][k] * W(n,k) + bias[n] ) * colscale[b][n] + coladd[b][n]
+ *
+ * A is [Bt][R][K], C is [Bt][R][N] (K % 8 == 0; N % 8 == 0 unless dtype is PB_F32).  bias, ascale,
+ * colscale, coladd are optional fp32 vectors (NULL = absent).  With ascale = the squeeze-excite gate
+ * this fuses `x * w` (mobilenet.py:25) into pointwise_conv2.
+ *
+ * _simt: fp32 W addressed as w[n*w_sn + k*w_sk] (so the same kernel serves fwd and dgrad); W is
+ *        rounded to the activation dtype first, like autocast does.
+ * _tc:   tcgen05/TMEM bf16 path; W is bf16 [Bw][N][K] (K contiguous) with Bw == 1 or Bw == Bt, e.g. the
+ *        per-sample gate-folded weights written by pb_fold_gate_bf16.
+ * ---------------------------------------------------------------------------------------------- */
+int pb_pw_gemm_simt(const void* A, const float* W, long long w_sn, long long w_sk, const float* bias,
+                    const float* ascale, const float* colscale, const float* coladd, void* C, int dtype,
+                    int Bt, long long R, int K, int N, pb_stream_t stream);
+int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const float* bias,
+                  const float* colscale, const float* coladd, void* C,
+                  int Bt, long long R, int K, int N, pb_stream_t stream);
+/* Weight gradient  dW[n][k] = sum_b ascale[b][k] * sum_r dC[b][r][n] * A[b][r][k]  (fp32, overwritten).
+ * Optionally also dbias[n] = sum dC (NULL to skip). */
+int pb_pw_wgrad_simt(const void* A, const void* dC, const float* ascale, float* dW, float* dbias,
+                     int dtype, int Bt, long long R, int K, int N, pb_stream_t stream);
+int pb_pw_wgrad_tc(const void* A, const void* dC, float* dW_partial, float* dW,
+                   int Bt, long long R, int K, int N, int per_batch, pb_stream_t stream);
+
+/* fp32 [rows][cols] -> dst (dtype) [cols][rows] if transpose else [rows][cols]. */
+int pb_cast_matrix(const float* src, void* dst, int dst_dtype, int rows, int cols, int transpose,
+                   pb_stream_t stream);
+/* dst[b][n][k] = bf16( W[n][k] * gate[b][k] )  -- squeeze-excite gate folded into pointwise_conv2. */
+int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, int Bt, int N, int K, pb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm3d/1d (+ activation + Dropout3d) -- mobilenet.py:80-82,90-92,142-143,180-181,247-248;
+ * movinet.py:65,75-76,93,141-143,150-152.  Training mode uses batch statistics over the M rows.
+ * ---------------------------------------------------------------------------------------------- */
+/* sums[0][c] = sum_m x, sums[1][c] = sum_m x^2 (fp64, overwritten). */
+int pb_colstats(const void* x, int dtype, long long M, int C, double* sums, pb_stream_t stream);
+/* training: mean/var from sums, running stats updated (momentum, unbiased var), else running stats.
+ * Writes scale = gamma*invstd, shift = beta - mean*scale, mean, invstd (all [C]). */
+int pb_bn_finalize(const double* sums, long long M, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, int training, float momentum, float eps,
+                   float* scale, float* shift, float* mean, float* invstd, int C, pb_stream_t stream);
+/* out = act(z*scale + shift) * mask[b][c]   (mask NULL = no dropout; mask holds 0 or 1/(1-p)). */
+int pb_bn_act_fwd(const void* z, const float* scale, const float* shift, const float* mask, void* out,
+                  int dtype, int B, long long R, int C, int act, float slope, pb_stream_t stream);
+/* Backward, pass 1: sums[0][c] = sum du, sums[1][c] = sum du*xhat with du = dout*mask*act'(u).
+ * dout is [B][R][C] of `dtype`, or (dout_bcast != 0) fp32 [B][C] broadcast over the R rows (the
+ * gradient of a global average pool, already divided by R). */
+int pb_bn_act_bwd_reduce(const void* dout, int dout_bcast, const void* z, const float* scale,
+                         const float* shift, const float* mean, const float* invstd, const float* mask,
+                         double* sums, int dtype, int B, long long R, int C, int act, float slope,
+                         pb_stream_t stream);
+/* dgamma = sums[1], dbeta = sums[0]; coef[0][c] = sums[0]/M, coef[1][c] = sums[1]/M (zeros in eval). */
+int pb_bn_bwd_finalize(const double* sums, long long M, int training, float* dgamma, float* dbeta,
+                       float* coef, int C, pb_stream_t stream);
+/* Pass 2: dz = scale * (du - coef0 - xhat*coef1). */
+int pb_bn_act_bwd_apply(const void* dout, int dout_bcast, const void* z, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, const float* mask,
+                        const float* coef, void* dz, int dtype, int B, long long R, int C, int act,
+                        float slope, pb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Squeeze-excite and global pooling -- SEBlock3D (mobilenet.py:11-26), AdaptiveAvgPool3d in the
+ * classifiers (mobilenet.py:186, 252; movinet.py:147).
+ * ---------------------------------------------------------------------------------------------- */
+int pb_pool_fwd(const void* x, int dtype, int B, long long R, int C, float* mean, pb_stream_t stream);
+/* hidden = relu(W1 mean + b1) [B][Ch];  gate = hardsigmoid(W2 hidden + b2) [B][C]. */
+int pb_se_fc_fwd(const float* mean, const float* W1, const float* b1, const float* W2, const float* b2,
+                 float* hidden, float* gate, int B, int C, int Ch, pb_stream_t stream);
+/* dgate [B][C] -> dmean [B][C] (already multiplied by inv_R) and fp32 parameter gradients (overwritten).
+ * work: caller-provided scratch of B*(C+Ch) floats. */
+int pb_se_fc_bwd(const float* dgate, const float* mean, const float* hidden, const float* gate,
+                 const float* W1, const float* W2, float inv_R, float* dmean, float* work,
+                 float* dW1, float* db1, float* dW2, float* db2, int B, int C, int Ch, pb_stream_t stream);
+int pb_rowscale(const void* x, const float* gate, void* y, int dtype, int B, long long R, int C,
+                pb_stream_t stream);                                      /* y = x * gate[b][c] */
+int pb_rowdot(const void* g, const void* y, int dtype, int B, long long R, int C, float* out,
+              pb_stream_t stream);                                        /* out[b][c] = sum_r g*y */
+int pb_scale_add(void* g, const float* gate, const float* add, int dtype, int B, long long R, int C,
+                 pb_stream_t stream);                                     /* g = g*gate[b][c] + add[b][c] */
+
+/* ------------------------------------------------------------------------------------------------
+ * Stem: dense Conv3d with tiny Cin.  Replaces block1.0 (mobilenet.py:141, 221: Conv3d(3,16,3,s2,p1)+bias;
+ * movinet.py:92: Conv3d(3,16,(1,3,3),s(1,2,2),p(0,1,1)), no bias) and fuses extract_features_labels'
+ * uint8 -> /255 conversion (train.py:106) when x_dtype == PB_U8 (in_div = 255; ignored otherwise).
+ *   x: logical (B,Cin,T,H,W) addressed with element strides xs_*; w fp32 (Cout,Cin,kT,kH,kW); y NDHWC.
+ * ---------------------------------------------------------------------------------------------- */
+int pb_stem_conv_fwd(const void* x, int x_dtype, long long xs_b, long long xs_c, long long xs_t,
+                     long long xs_h, long long xs_w, float in_div, const float* w, const float* bias,
+                     void* y, int y_dtype, int B, int Cin, int T, int H, int W, int Cout,
+                     int kT, int kH, int kW, int sT, int sH, int sW, int pT, int pH, int pW,
+                     int To, int Ho, int Wo, pb_stream_t stream);
+int pb_stem_conv_wgrad(const void* x, int x_dtype, long long xs_b, long long xs_c, long long xs_t,
+                       long long xs_h, long long xs_w, float in_div, const void* dy, int y_dtype,
+                       float* dw, float* dbias, int B, int Cin, int T, int H, int W, int Cout,
+                       int kT, int kH, int kW, int sT, int sH, int sW, int pT, int pH, int pW,
+                       int To, int Ho, int Wo, pb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICKLEBOT_B200_H */

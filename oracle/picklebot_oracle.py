@@ -224,6 +224,54 @@ def causal_conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Te
     return F.conv3d(x, weight, bias, stride, padding, dilation, groups)
 
 
+def movinet_a2_stream(sd: SD, chunks: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """Causal, chunked MoViNetA2 inference -- PARITY UNPINNED BY THE REFERENCE (movinet.py never wires
+    CausalConv3d or its buffers into MoViNetA2; SURVEY.md finding 5).  This restates the specification the
+    build adopted (picklebot_b200/movinet.py docstring) with reference ops so the CUDA path has a checker:
+      * every depthwise conv is a CausalConv3d (movinet.py:23-39): left pad kT-1, and across chunks the pad
+        frames are the previous chunk's last kT-1 *input* frames (zeros before the first chunk);
+      * squeeze-excite means and the classifier pool are cumulative over all frames seen so far;
+      * BatchNorm in eval mode, dropouts off.
+    Returns the logits after each chunk."""
+    blocks_ = [(f"{blk}.{i}.", row) for blk, rows in MOVINET_A2_BLOCKS.items() for i, row in enumerate(rows)]
+    state = [dict() for _ in blocks_]
+    head_sum, head_n, outs = None, 0, []
+    for x in chunks:
+        x = F.conv3d(x, sd["block1.0.weight"], None, (1, 2, 2), (0, 1, 1))
+        x = F.hardswish(_bn(sd, "block1.1.", x, False))
+        for (prefix, (_, _, _, k, s, p)), st in zip(blocks_, state):
+            x = F.conv3d(x, sd[prefix + "expand.weight"])
+            if k[0] > 1:
+                prev = st.get("buf")
+                if prev is None:
+                    prev = x.new_zeros(x.shape[0], x.shape[1], k[0] - 1, x.shape[3], x.shape[4])
+                xin = torch.cat([prev, x], 2)
+                st["buf"] = xin[:, :, xin.shape[2] - (k[0] - 1):].clone()
+            else:
+                xin = x
+            x = F.conv3d(xin, sd[prefix + "conv.weight"], None, s, (0, p[1], p[2]), 1, x.shape[1])
+            n = x.shape[2] * x.shape[3] * x.shape[4]
+            ssum = x.sum((2, 3, 4))
+            st["sum"] = ssum if "sum" not in st else st["sum"] + ssum
+            st["n"] = st.get("n", 0) + n
+            w = (st["sum"] / st["n"]).view(x.shape[0], -1, 1, 1, 1)
+            se = prefix + "squeeze_excite.se."
+            w = F.relu(F.conv3d(w, sd[se + "1.weight"], sd[se + "1.bias"]))
+            w = F.hardsigmoid(F.conv3d(w, sd[se + "3.weight"], sd[se + "3.bias"]))
+            x = F.conv3d(x * w, sd[prefix + "project.weight"])
+            x = F.hardswish(_bn(sd, prefix + "batchnorm.", x, False))
+        x = F.hardswish(_bn(sd, "conv.1.", F.conv3d(x, sd["conv.0.weight"]), False))
+        n = x.shape[2] * x.shape[3] * x.shape[4]
+        hsum = x.sum((2, 3, 4))
+        head_sum = hsum if head_sum is None else head_sum + hsum
+        head_n += n
+        f = head_sum / head_n
+        f = F.linear(f, sd["classifier.2.weight"], sd["classifier.2.bias"])
+        f = F.hardswish(_bn(sd, "classifier.3.", f, False))
+        outs.append(F.linear(f, sd["classifier.6.weight"], sd["classifier.6.bias"]))
+    return outs
+
+
 MODELS = {
     "MobileNetLarge3D": mobilenet_large3d,
     "MobileNetSmall3D": mobilenet_small3d,

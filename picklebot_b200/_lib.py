@@ -1,0 +1,92 @@
+"""ctypes binding of libpicklebot_b200.so (C ABI declared in include/picklebot_b200.h).
+
+The product path has no CPU or library fallback: if the shared library is missing, or a call
+returns a non-zero code, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpicklebot_b200.so")
+
+PB_OK = 0
+PB_F32, PB_BF16, PB_U8, PB_F32_RBF16 = 0, 1, 2, 16
+ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_LRELU, ACT_HSIGMOID = 0, 1, 2, 3, 4
+
+_P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+_T = {"p": _P, "i": _I, "l": _L, "f": _F}
+
+# name -> argument type string (p = pointer, i = int, l = long long, f = float); all return int
+_DW = "pppi" + "i" * 17 + "p"
+SIGNATURES = {
+    "pb_dwconv3d_fwd": _DW,
+    "pb_dwconv3d_dgrad": _DW,
+    "pb_dwconv3d_wgrad": _DW,
+    "pb_stream_dwconv3d_fwd": "pppppi" + "i" * 14 + "p",
+    "pb_pw_gemm_simt": "ppllpppppiiliip",
+    "pb_pw_gemm_tc": "ppipppp" + "iliip",
+    "pb_pw_wgrad_simt": "pppppiiliip",
+    "pb_pw_wgrad_tc": "ppppiliiip",
+    "pb_cast_matrix": "ppiiiip",
+    "pb_fold_gate_bf16": "pppiiip",
+    "pb_colstats": "pilipp",
+    "pb_bn_finalize": "plppppiffppppip",
+    "pb_bn_act_fwd": "pppppiiliifp",
+    "pb_bn_act_bwd_reduce": "pippppppp" + "iiliifp",
+    "pb_bn_bwd_finalize": "plipppip",
+    "pb_bn_act_bwd_apply": "pipppppppp" + "iiliifp",
+    "pb_pool_fwd": "piilipp",
+    "pb_se_fc_fwd": "pppppppiiip",
+    "pb_se_fc_bwd": "ppppppfpppppp" + "iiip",
+    "pb_rowscale": "pppiilip",
+    "pb_rowdot": "ppiilipp",
+    "pb_scale_add": "pppiilip",
+    "pb_stem_conv_fwd": "pi" + "lllll" + "f" + "pppi" + "i" * 18 + "p",
+    "pb_stem_conv_wgrad": "pi" + "lllll" + "f" + "pipp" + "i" * 18 + "p",
+}
+PLAIN = ("pb_abi_version", "pb_last_error_string", "pb_launch_count", "pb_device_check")
+EXPORTS = tuple(SIGNATURES) + PLAIN
+
+
+class PicklebotKernelError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+            "`python picklebot_b200/csrc/build.py` (or __graft_entry__.build()). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, sig in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = [_T[c] for c in sig]
+        fn.restype = _I
+    lib.pb_abi_version.restype = _I
+    lib.pb_last_error_string.restype = ctypes.c_char_p
+    lib.pb_launch_count.restype = _L
+    lib.pb_device_check.restype = _I
+    return lib
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    rc = getattr(lib(), name)(*args)
+    if rc != PB_OK:
+        msg = lib().pb_last_error_string()
+        raise PicklebotKernelError(f"{name} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(lib().pb_launch_count())

@@ -1,0 +1,360 @@
+"""Fused forward/backward of the building blocks, as torch.autograd.Functions over the CUDA kernels.
+
+One autograd node per bottleneck (not per op): the block owns its intermediate tensors, so what is
+saved for backward and how ops are fused is decided here, and DDP's bucketed all-reduce still overlaps
+with the backward of earlier blocks because parameter gradients become ready block by block.
+
+Tensors crossing a block boundary are ordinary ``(B, C, T, H, W)`` torch tensors with channels-last-3d
+strides (a zero-copy permute of the NDHWC buffer the kernels work on), so the modules stay drop-in.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+from .ops import ACT_CODES
+
+
+# ---------------------------------------------------------------------------------------------
+# layout helpers
+# ---------------------------------------------------------------------------------------------
+def to_ndhwc(x: torch.Tensor) -> torch.Tensor:
+    """(B,C,T,H,W) any strides -> contiguous (B,T,H,W,C).  Zero-copy when x is channels-last-3d."""
+    y = x.permute(0, 2, 3, 4, 1)
+    return y if y.is_contiguous() else y.contiguous()
+
+
+def from_ndhwc(y: torch.Tensor) -> torch.Tensor:
+    return y.permute(0, 4, 1, 2, 3)
+
+
+def compute_dtype(x: torch.Tensor) -> torch.dtype:
+    """Activation storage type: the autocast dtype when autocast is on (train.py:264), else x's own."""
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+        if dt != torch.bfloat16:
+            raise RuntimeError(f"picklebot_b200 supports bf16 autocast only, got {dt}")
+        return dt
+    if x.dtype in (torch.float32, torch.bfloat16):
+        return x.dtype
+    if x.dtype == torch.uint8:
+        return torch.bfloat16
+    raise TypeError(f"unsupported input dtype {x.dtype}")
+
+
+class WeightCache:
+    """Repacked / cast shadow copies of parameters, refreshed when the parameter changes
+    (optimizer steps bump ``_version``; ``.to()`` / load_state_dict change data_ptr or version)."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, param: torch.Tensor, maker):
+        tag = (param.data_ptr(), param._version, param.device)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        val = maker()
+        self._store[key] = (tag, val)
+        return val
+
+    def clear(self):
+        self._store.clear()
+
+
+@dataclass(frozen=True)
+class BlockCfg:
+    k: Tuple[int, int, int]
+    s: Tuple[int, int, int]
+    p: Tuple[int, int, int]
+    act: int
+    slope: float
+    use_se: bool
+    p_drop: float
+    eps: float
+    momentum: float
+
+
+def draw_dropout3d_mask(B: int, C: int, p: float, dtype: torch.dtype, device) -> torch.Tensor:
+    """Same generator calls as aten::feature_dropout behind nn.Dropout3d (mobilenet.py:82,92): noise of
+    shape (B,C,1,1,1) in the activation dtype, bernoulli_(1-p) then div_(1-p).  Returned as fp32 [B][C]."""
+    noise = torch.empty((B, C, 1, 1, 1), dtype=dtype, device=device).bernoulli_(1 - p).div_(1 - p)
+    return noise.view(B, C).float()
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMM front-ends (pick tcgen05 or CUDA-core kernel)
+# ---------------------------------------------------------------------------------------------
+def _w2d(w: torch.Tensor) -> torch.Tensor:
+    return w.detach().reshape(w.shape[0], -1)
+
+
+def pw_fwd(A: torch.Tensor, w: torch.Tensor, cache: WeightCache, key: str, bias=None, gate=None, Bt: int = 1
+           ) -> torch.Tensor:
+    """[rows][K] x W[N][K]^T (+bias); gate [Bt][K] scales A's columns per sample (squeeze-excite)."""
+    W = _w2d(w)
+    N, K = W.shape
+    if ops.use_tc(A.dtype, K, N):
+        from . import gemm_tc
+        if gate is not None:
+            Wb = ops.fold_gate(W, gate)
+            return gemm_tc.gemm(A, Wb, N, K, Bw=Bt, Bt=Bt, bias=bias)
+        Wb = cache.get((key, "bf16"), w, lambda: ops.cast_matrix(W, N, K, torch.bfloat16))
+        return gemm_tc.gemm(A, Wb, N, K, Bw=1, Bt=1, bias=bias)
+    return ops.gemm_simt(A, W, N, K, K, 1, bias=bias, ascale=gate, Bt=Bt)
+
+
+def pw_dgrad(dC: torch.Tensor, w: torch.Tensor, cache: WeightCache, key: str) -> torch.Tensor:
+    """dA[rows][K] = dC[rows][N] x W[N][K]."""
+    W = _w2d(w)
+    N, K = W.shape
+    if ops.use_tc(dC.dtype, N, K):
+        from . import gemm_tc
+        Wt = cache.get((key, "bf16_t"), w, lambda: ops.cast_matrix(W, N, K, torch.bfloat16, transpose=True))
+        return gemm_tc.gemm(dC, Wt, K, N, Bw=1, Bt=1)
+    return ops.gemm_simt(dC, W, K, N, 1, K)
+
+
+def pw_wgrad(A: torch.Tensor, dC: torch.Tensor, w: torch.Tensor, gate=None, Bt: int = 1, want_bias: bool = False):
+    W = _w2d(w)
+    N, K = W.shape
+    if ops.use_tc(A.dtype, K, N) and gate is None and not want_bias:
+        from . import gemm_tc
+        if gemm_tc.wgrad_ready():
+            return gemm_tc.wgrad(A, dC, K, N).view(w.shape), None
+    dW, db = ops.wgrad_simt(A, dC, K, N, ascale=gate, Bt=Bt, want_bias=want_bias)
+    return dW.view(w.shape), db
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm(+act+dropout) helper shared by every block
+# ---------------------------------------------------------------------------------------------
+def bn_forward(z: torch.Tensor, B: int, C: int, gamma, beta, rmean, rvar, nbt, training: bool, eps: float,
+               momentum: float, act: int, slope: float, mask):
+    """z: NDHWC/2-D activations with C channels.  Returns (out, (scale, shift, mean, invstd))."""
+    M = z.numel() // C
+    use_batch = training or rmean is None
+    sums = ops.colstats(z, C) if use_batch else None
+    scale, shift, mean, invstd = ops.bn_finalize(sums, M, gamma, beta, rmean, rvar, use_batch, momentum, eps, C,
+                                                 z.device)
+    if use_batch and nbt is not None:
+        nbt.add_(1)
+    out = ops.bn_act_fwd(z, scale, shift, mask, B, C, act, slope)
+    return out, (scale, shift, mean, invstd)
+
+
+# ---------------------------------------------------------------------------------------------
+# inverted-residual bottleneck: pw1 -> depthwise -> [SE] -> pw2 -> BN -> act -> Dropout3d
+# (Bottleneck3D.forward mobilenet.py:84-93; MoviNetBottleneck.forward movinet.py:69-77)
+# ---------------------------------------------------------------------------------------------
+class BottleneckFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cfg: BlockCfg, cache: WeightCache, training: bool, mask, rmean, rvar, nbt,
+                w1, wdw, w2, gamma, beta, se_w1, se_b1, se_w2, se_b2):
+        x5 = to_ndhwc(x)
+        B, T, H, W, Cin = x5.shape
+        Cexp, Cout = w1.shape[0], w2.shape[0]
+        dt = x5.dtype
+        y1 = pw_fwd(x5.view(-1, Cin), w1, cache, "w1").view(B, T, H, W, Cexp)
+        wdw_tc = cache.get(("wdw", dt), wdw, lambda: ops.dw_weight_tapmajor(wdw, dt))
+        y2 = ops.dwconv_fwd(y1, wdw_tc, cfg.k, cfg.s, cfg.p)
+        _, To, Ho, Wo, _ = y2.shape
+        pooled = hidden = gate = None
+        if cfg.use_se:
+            pooled = ops.pool_fwd(y2, B, Cexp)
+            hidden, gate = ops.se_fc_fwd(pooled, _w2d(se_w1), se_b1.detach(), _w2d(se_w2), se_b2.detach())
+        z = pw_fwd(y2.view(-1, Cexp), w2, cache, "w2", gate=gate, Bt=B if gate is not None else 1)
+        out, bn_state = bn_forward(z, B, Cout, gamma.detach(), beta.detach(), rmean, rvar, nbt, training, cfg.eps,
+                                   cfg.momentum, cfg.act, cfg.slope, mask)
+        ctx.cfg, ctx.cache, ctx.training = cfg, cache, training
+        ctx.shapes = (B, T, H, W, Cin, Cexp, Cout, To, Ho, Wo)
+        ctx.save_for_backward(x5, y1, y2, z, mask, pooled, hidden, gate, *bn_state,
+                              w1, wdw, w2, se_w1, se_w2, wdw_tc)
+        return from_ndhwc(out.view(B, To, Ho, Wo, Cout))
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x5, y1, y2, z, mask, pooled, hidden, gate, scale, shift, mean, invstd,
+         w1, wdw, w2, se_w1, se_w2, wdw_tc) = ctx.saved_tensors
+        cfg, cache = ctx.cfg, ctx.cache
+        B, T, H, W, Cin, Cexp, Cout, To, Ho, Wo = ctx.shapes
+        d5 = to_ndhwc(dout)
+        if d5.dtype != z.dtype:
+            d5 = d5.to(z.dtype)
+        dz, dgamma, dbeta = ops.bn_act_bwd(d5, False, z, scale, shift, mean, invstd, mask, B, Cout, cfg.act,
+                                           ctx.training, cfg.slope)
+        dw2, _ = pw_wgrad(y2.view(-1, Cexp), dz, w2, gate=gate, Bt=B if gate is not None else 1)
+        g = pw_dgrad(dz, w2, cache, "w2")                       # d(y2 * gate)  [M'][Cexp]
+        dse = (None, None, None, None)
+        if cfg.use_se:
+            dgate = ops.rowdot(g, y2, B, Cexp)
+            dmean, dW1, db1, dW2, db2 = ops.se_fc_bwd(dgate, pooled, hidden, gate, _w2d(se_w1), _w2d(se_w2),
+                                                      1.0 / float(To * Ho * Wo))
+            ops.scale_add_(g, gate, dmean, B, Cexp)             # dy2 = g*gate + dmean/R
+            dse = (dW1.view(se_w1.shape), db1, dW2.view(se_w2.shape), db2)
+        dy2 = g.view(B, To, Ho, Wo, Cexp)
+        dwdw_tc = ops.dwconv_wgrad(y1, dy2, cfg.k, cfg.s, cfg.p)
+        dwdw = ops.dw_weight_grad_from_tapmajor(dwdw_tc, wdw.shape)
+        dy1 = ops.dwconv_dgrad(dy2, wdw_tc, y1.shape, cfg.k, cfg.s, cfg.p)
+        dw1, _ = pw_wgrad(x5.view(-1, Cin), dy1.view(-1, Cexp), w1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = from_ndhwc(pw_dgrad(dy1.view(-1, Cexp), w1, cache, "w1").view(B, T, H, W, Cin))
+        return (dx, None, None, None, None, None, None, None,
+                dw1, dwdw, dw2, dgamma, dbeta, *dse)
+
+
+# ---------------------------------------------------------------------------------------------
+# stem: Conv3d(3->16) [+bias] -> BN -> Hardswish   (mobilenet.py:140-144; movinet.py:91-95)
+# ---------------------------------------------------------------------------------------------
+class StemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, s, p, dt, training, eps, momentum, rmean, rvar, nbt, w, bias, gamma, beta):
+        B = x.shape[0]
+        Cout = w.shape[0]
+        if x.dtype not in (torch.uint8, torch.float32, torch.bfloat16):
+            raise TypeError(f"stem: unsupported clip dtype {x.dtype}")
+        z = ops.stem_fwd(x, w.detach().contiguous(), None if bias is None else bias.detach(), k, s, p, dt)
+        out, bn_state = bn_forward(z, B, Cout, gamma.detach(), beta.detach(), rmean, rvar, nbt, training, eps,
+                                   momentum, ACT_CODES["hswish"], 0.0, None)
+        ctx.conv = (k, s, p)
+        ctx.training = training
+        ctx.has_bias = bias is not None
+        ctx.wshape = w.shape
+        ctx.save_for_backward(x, z, *bn_state)
+        return from_ndhwc(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, z, scale, shift, mean, invstd = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("picklebot_b200: gradient w.r.t. the input clip is not implemented")
+        k, s, p = ctx.conv
+        B, Cout = z.shape[0], z.shape[-1]
+        d5 = to_ndhwc(dout)
+        if d5.dtype != z.dtype:
+            d5 = d5.to(z.dtype)
+        dz, dgamma, dbeta = ops.bn_act_bwd(d5, False, z, scale, shift, mean, invstd, None, B, Cout,
+                                           ACT_CODES["hswish"], ctx.training)
+        dw, db = ops.stem_wgrad(x, dz, ctx.wshape, k, s, p, ctx.has_bias)
+        return (None,) * 11 + (dw, db, dgamma, dbeta)
+
+
+# ---------------------------------------------------------------------------------------------
+# tail of the MobileNets: 1x1x1 conv (+bias) [-> SE] -> BN -> Hardswish -> global pool -> FC -> Hardswish -> FC
+# (mobilenet.py:178-190 Large; 244-256 Small, where SE sits between the conv and the BN)
+# ---------------------------------------------------------------------------------------------
+class MobileNetTailFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cache: WeightCache, training, eps, momentum, use_se, rmean, rvar, nbt,
+                wc, bc, gamma, beta, wf1, bf1, wf2, bf2, se_w1, se_b1, se_w2, se_b2):
+        x5 = to_ndhwc(x)
+        B, T, H, W, Cin = x5.shape
+        Cmid = wc.shape[0]
+        R = T * H * W
+        hs = ACT_CODES["hswish"]
+        z0 = pw_fwd(x5.view(-1, Cin), wc, cache, "tail_conv", bias=bc.detach())
+        pooled = hidden = gate = None
+        z = z0
+        if use_se:
+            pooled = ops.pool_fwd(z0, B, Cmid)
+            hidden, gate = ops.se_fc_fwd(pooled, _w2d(se_w1), se_b1.detach(), _w2d(se_w2), se_b2.detach())
+            z = ops.rowscale(z0, gate, B, Cmid)
+        a, bn_state = bn_forward(z, B, Cmid, gamma.detach(), beta.detach(), rmean, rvar, nbt, training, eps, momentum,
+                                 hs, 0.0, None)
+        feat = ops.pool_fwd(a, B, Cmid)                                   # fp32 [B][Cmid]
+        F1, NC = wf1.shape[0], wf2.shape[0]
+        u1 = ops.gemm_simt(feat, _w2d(wf1), F1, Cmid, Cmid, 1, bias=bf1.detach())
+        ones = torch.ones(F1, dtype=torch.float32, device=x.device)
+        zeros = torch.zeros(F1, dtype=torch.float32, device=x.device)
+        h1 = ops.bn_act_fwd(u1, ones, zeros, None, B, F1, hs)
+        logits = ops.gemm_simt(h1, _w2d(wf2), NC, F1, F1, 1, bias=bf2.detach())
+        ctx.cache, ctx.training, ctx.use_se = cache, training, use_se
+        ctx.shapes = (B, T, H, W, Cin, Cmid, R, F1, NC)
+        ctx.save_for_backward(x5, z0, z, pooled, hidden, gate, *bn_state, feat, u1, h1, ones, zeros,
+                              wc, wf1, wf2, se_w1, se_w2)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        (x5, z0, z, pooled, hidden, gate, scale, shift, mean, invstd, feat, u1, h1, ones, zeros,
+         wc, wf1, wf2, se_w1, se_w2) = ctx.saved_tensors
+        cache = ctx.cache
+        B, T, H, W, Cin, Cmid, R, F1, NC = ctx.shapes
+        hs = ACT_CODES["hswish"]
+        dl = dlogits.contiguous().float()
+        dwf2, dbf2 = ops.wgrad_simt(h1, dl, F1, NC, want_bias=True)
+        dh1 = ops.gemm_simt(dl, _w2d(wf2), F1, NC, 1, F1)
+        du1, _, _ = ops.bn_act_bwd(dh1, False, u1, ones, zeros, zeros, ones, None, B, F1, hs, False)
+        dwf1, dbf1 = ops.wgrad_simt(feat, du1, Cmid, F1, want_bias=True)
+        dfeat = ops.gemm_simt(du1, _w2d(wf1), Cmid, F1, 1, Cmid)           # [B][Cmid] fp32
+        dfeat.mul_(1.0 / R)                                                # gradient of the mean
+        dz, dgamma, dbeta = ops.bn_act_bwd(dfeat, True, z, scale, shift, mean, invstd, None, B, Cmid, hs,
+                                           ctx.training)
+        dse = (None, None, None, None)
+        if ctx.use_se:
+            dgate = ops.rowdot(dz, z0, B, Cmid)
+            dmean, dW1, db1, dW2, db2 = ops.se_fc_bwd(dgate, pooled, hidden, gate, _w2d(se_w1), _w2d(se_w2), 1.0 / R)
+            ops.scale_add_(dz, gate, dmean, B, Cmid)                       # dz0 = dz*gate + dmean/R
+            dse = (dW1.view(se_w1.shape), db1, dW2.view(se_w2.shape), db2)
+        dwc, dbc = pw_wgrad(x5.view(-1, Cin), dz, wc, want_bias=True)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = from_ndhwc(pw_dgrad(dz, wc, cache, "tail_conv").view(B, T, H, W, Cin))
+        return (dx, None, None, None, None, None, None, None, None,
+                dwc, dbc, dgamma, dbeta, dwf1.view(wf1.shape), dbf1, dwf2.view(wf2.shape), dbf2, *dse)
+
+
+# ---------------------------------------------------------------------------------------------
+# tail of MoViNetA2: conv 144->640 -> BN -> Hardswish -> Dropout3d -> pool -> Linear -> BN1d -> Hardswish
+# -> Dropout -> Linear   (movinet.py:139-154)
+# ---------------------------------------------------------------------------------------------
+class MoViNetTailFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cache: WeightCache, training, eps, momentum, mask3d, mask1d,
+                rmean, rvar, nbt, rmean1, rvar1, nbt1,
+                wc, gamma, beta, wf1, bf1, gamma1, beta1, wf2, bf2):
+        x5 = to_ndhwc(x)
+        B, T, H, W, Cin = x5.shape
+        Cmid = wc.shape[0]
+        R = T * H * W
+        hs = ACT_CODES["hswish"]
+        z = pw_fwd(x5.view(-1, Cin), wc, cache, "tail_conv")
+        a, bn_state = bn_forward(z, B, Cmid, gamma.detach(), beta.detach(), rmean, rvar, nbt, training, eps, momentum,
+                                 hs, 0.0, mask3d)
+        feat = ops.pool_fwd(a, B, Cmid)
+        F1, NC = wf1.shape[0], wf2.shape[0]
+        u1 = ops.gemm_simt(feat, wf1.detach(), F1, Cmid, Cmid, 1, bias=bf1.detach())
+        h1, bn1_state = bn_forward(u1, B, F1, gamma1.detach(), beta1.detach(), rmean1, rvar1, nbt1, training, eps,
+                                   momentum, hs, 0.0, mask1d)
+        logits = ops.gemm_simt(h1, wf2.detach(), NC, F1, F1, 1, bias=bf2.detach())
+        ctx.cache, ctx.training = cache, training
+        ctx.shapes = (B, T, H, W, Cin, Cmid, R, F1, NC)
+        ctx.save_for_backward(x5, z, mask3d, mask1d, *bn_state, feat, u1, *bn1_state, h1, wc, wf1, wf2)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        (x5, z, mask3d, mask1d, scale, shift, mean, invstd, feat, u1, scale1, shift1, mean1, invstd1, h1,
+         wc, wf1, wf2) = ctx.saved_tensors
+        cache = ctx.cache
+        B, T, H, W, Cin, Cmid, R, F1, NC = ctx.shapes
+        hs = ACT_CODES["hswish"]
+        dl = dlogits.contiguous().float()
+        dwf2, dbf2 = ops.wgrad_simt(h1, dl, F1, NC, want_bias=True)
+        dh1 = ops.gemm_simt(dl, wf2.detach(), F1, NC, 1, F1)
+        du1, dgamma1, dbeta1 = ops.bn_act_bwd(dh1, False, u1, scale1, shift1, mean1, invstd1, mask1d, B, F1, hs,
+                                              ctx.training)
+        dwf1, dbf1 = ops.wgrad_simt(feat, du1, Cmid, F1, want_bias=True)
+        dfeat = ops.gemm_simt(du1, wf1.detach(), Cmid, F1, 1, Cmid)
+        dfeat.mul_(1.0 / R)
+        dz, dgamma, dbeta = ops.bn_act_bwd(dfeat, True, z, scale, shift, mean, invstd, mask3d, B, Cmid, hs,
+                                           ctx.training)
+        dwc, _ = pw_wgrad(x5.view(-1, Cin), dz, wc)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = from_ndhwc(pw_dgrad(dz, wc, cache, "tail_conv").view(B, T, H, W, Cin))
+        return (dx,) + (None,) * 12 + (dwc, dgamma, dbeta, dwf1, dbf1, dgamma1, dbeta1, dwf2, dbf2)

@@ -1,0 +1,58 @@
+// Column reductions over NDHWC matrices X[nbatch][R][C]: every thread owns 8 channels and strides over
+// rows; fp32 per-thread partials -> shared-memory atomics per CTA -> one global atomic per (value,
+// channel) per CTA (fp64 for BatchNorm statistics, fp32 for pooling).
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+// F: struct with  __device__ void operator()(int batch, long long row_in_batch, int c0, float (&out)[NV][8]) const
+template <typename F, int NV, typename OUT>
+__global__ void __launch_bounds__(256)
+colreduce_kernel(F f, long long R, int C, OUT* __restrict__ out, int nbatch, float out_scale) {
+    extern __shared__ float sm_red[];   // [NV][C]
+    const int G = C >> 3;
+    const int RPI = blockDim.x / G;
+    const int g = threadIdx.x % G, rr = threadIdx.x / G;
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < NV * C; i += blockDim.x) sm_red[i] = 0.f;
+    __syncthreads();
+    if (rr < RPI) {
+        float acc[NV][8];
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
+        const int c0 = g << 3;
+        for (long long r = (long long)blockIdx.x * RPI + rr; r < R; r += (long long)gridDim.x * RPI) {
+            float t[NV][8];
+            f(b, r, c0, t);
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[v][i] += t[v][i];
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(&sm_red[v * C + c0 + i], acc[v][i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NV * C; i += blockDim.x) {
+        int v = i / C, c = i % C;
+        atomicAdd(&out[((long long)v * nbatch + b) * C + c], (OUT)(sm_red[i] * out_scale));
+    }
+}
+
+// grid sizing: enough CTAs to fill the machine, never more than one CTA per RPI rows
+static inline dim3 colreduce_grid(long long R, int C, int nbatch) {
+    int G = C >> 3;
+    int RPI = 256 / G;
+    long long max_ctas = (R + RPI - 1) / RPI;
+    long long want = (148LL * 8 + nbatch - 1) / nbatch;
+    int gx = (int)(max_ctas < want ? max_ctas : want);
+    if (gx < 1) gx = 1;
+    return dim3(gx, nbatch);
+}
+
+}  // namespace pb

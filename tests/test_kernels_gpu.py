@@ -1,0 +1,252 @@
+"""Per-kernel parity on the B200: every C-ABI entry point against the same op written with torch
+(fp32 math on the GPU, TF32 off).  fp32 storage must agree to 1e-4 (norm-wise), bf16 storage to 1e-2."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def tol(dt):
+    return 1e-4 if dt == torch.float32 else 1e-2
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def rnd(*shape, dt=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return ((torch.rand(*shape, generator=g) * 2 - 1) * scale).cuda().to(dt)
+
+
+DW_CASES = [
+    # B, C, T, H, W, k, s, p
+    (2, 16, 4, 12, 12, (1, 3, 3), (1, 1, 1), (1, 1, 1)),      # mobilenet k3 s1: time padded
+    (2, 64, 5, 13, 11, (1, 3, 3), (2, 2, 2), (1, 1, 1)),      # mobilenet k3 s2: time strided, odd sizes
+    (2, 72, 4, 14, 14, (1, 5, 5), (2, 2, 2), (2, 2, 2)),      # k5 s2
+    (1, 120, 3, 7, 7, (1, 5, 5), (1, 1, 1), (2, 2, 2)),       # k5 s1 small spatial
+    (2, 40, 6, 9, 9, (3, 3, 3), (1, 1, 1), (1, 1, 1)),        # movinet 3x3x3
+    (1, 96, 6, 10, 10, (3, 3, 3), (1, 2, 2), (1, 1, 1)),      # movinet 3x3x3 spatial stride
+    (1, 240, 7, 6, 6, (5, 3, 3), (1, 2, 2), (2, 1, 1)),       # movinet 5x3x3
+    (1, 960, 3, 7, 7, (1, 5, 5), (1, 1, 1), (2, 2, 2)),       # widest layer
+    (2, 8, 1, 1, 1, (1, 3, 3), (1, 1, 1), (1, 1, 1)),         # degenerate 1x1x1 frame
+]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", DW_CASES)
+def test_dwconv_fwd_dgrad_wgrad(case, dt):
+    from picklebot_b200 import ops
+    B, C, T, H, W, k, s, p = case
+    x = rnd(B, T, H, W, C, dt=dt, seed=1)
+    w = rnd(C, 1, *k, seed=2, scale=0.5)
+    w_tc = ops.dw_weight_tapmajor(w, dt)
+    y = ops.dwconv_fwd(x, w_tc, k, s, p)
+    # torch reference in fp32 on the same (rounded) operands
+    xr = x.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    wr = w.to(dt).float().requires_grad_(True)
+    yr = F.conv3d(xr, wr, None, s, p, 1, C)
+    assert tuple(y.shape) == tuple(yr.permute(0, 2, 3, 4, 1).shape)
+    assert rel_err(y.float(), yr.permute(0, 2, 3, 4, 1)) < tol(dt)
+    dy = rnd(*y.shape, dt=dt, seed=3)
+    yr.backward(dy.float().permute(0, 4, 1, 2, 3))
+    dx = ops.dwconv_dgrad(dy, w_tc, x.shape, k, s, p)
+    assert rel_err(dx.float(), xr.grad.permute(0, 2, 3, 4, 1)) < tol(dt)
+    dw_tc = ops.dwconv_wgrad(x, dy, k, s, p)
+    dw = ops.dw_weight_grad_from_tapmajor(dw_tc, w.shape)
+    assert rel_err(dw, wr.grad) < (1e-4 if dt == torch.float32 else 2e-3)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("kt", [1, 3, 5])
+def test_stream_dwconv_chunking_invariance(kt, dt):
+    """8 chunks through the stream kernel == one causal pass (F.pad left by kT-1, movinet.py:34-39)."""
+    from picklebot_b200 import ops
+    B, C, T, H, W = 2, 24, 12, 9, 9
+    k, s, p = (kt, 3, 3), (1, 2, 2), (0, 1, 1)
+    x = rnd(B, T, H, W, C, dt=dt, seed=4)
+    w = rnd(C, 1, *k, seed=5, scale=0.5)
+    w_tc = ops.dw_weight_tapmajor(w, dt)
+    xr = F.pad(x.float().permute(0, 4, 1, 2, 3), (0, 0, 0, 0, kt - 1, 0))
+    yr = F.conv3d(xr, w.to(dt).float(), None, s, p, 1, C).permute(0, 2, 3, 4, 1)
+    outs, buf = [], None
+    for chunk in (x[:, :5], x[:, 5:6], x[:, 6:]):     # ragged chunks, one shorter than kT-1
+        y, buf = ops.stream_dwconv_fwd(chunk.contiguous(), buf, w_tc, k, s, p)
+        outs.append(y)
+    y = torch.cat(outs, 1)
+    assert rel_err(y.float(), yr) < tol(dt)
+    whole, _ = ops.stream_dwconv_fwd(x, None, w_tc, k, s, p)
+    assert torch.equal(whole, y)                      # chunking is bit-exact
+
+
+GEMM_CASES = [(1, 300, 16, 16), (1, 1000, 24, 72), (3, 131, 72, 40), (2, 257, 960, 160), (1, 64, 960, 1280),
+              (1, 64, 1280, 2), (1, 5, 8, 13)]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", GEMM_CASES)
+def test_gemm_simt_fwd_dgrad_wgrad(case, dt):
+    from picklebot_b200 import ops
+    Bt, R, K, N = case
+    if dt == torch.bfloat16 and (N % 8 or K % 8):
+        pytest.skip("bf16 activations need channel counts that are multiples of 8")
+    A = rnd(Bt * R, K, dt=dt, seed=1)
+    W = rnd(N, K, seed=2, scale=0.3)
+    bias = rnd(N, seed=3)
+    gate = (rnd(Bt, K, seed=4).abs() + 0.1).contiguous()
+    Wr = W.to(dt).float()
+    Ar = A.float().view(Bt, R, K)
+    # forward with gate + bias
+    C = ops.gemm_simt(A, W, N, K, K, 1, bias=bias, ascale=gate, Bt=Bt)
+    As = (Ar * gate[:, None, :]).to(dt).float()
+    Cr = As @ Wr.t() + bias
+    assert rel_err(C.float().view(Bt, R, N), Cr) < tol(dt)
+    # epilogue scale/add
+    cs, ca = rnd(Bt, N, seed=5), rnd(Bt, N, seed=6)
+    C2 = ops.gemm_simt(A, W, N, K, K, 1, colscale=cs, coladd=ca, Bt=Bt)
+    Cr2 = (Ar @ Wr.t()) * cs[:, None, :] + ca[:, None, :]
+    assert rel_err(C2.float().view(Bt, R, N), Cr2) < tol(dt)
+    # dgrad form: dA = dC x W
+    dC = rnd(Bt * R, N, dt=dt, seed=7)
+    dA = ops.gemm_simt(dC, W, K, N, 1, K)
+    assert rel_err(dA.float(), dC.float() @ Wr) < tol(dt)
+    # wgrad with gate and bias
+    dW, db = ops.wgrad_simt(A, dC, K, N, ascale=gate, Bt=Bt, want_bias=True)
+    dWr = torch.einsum("brn,brk->nk", dC.float().view(Bt, R, N), As)
+    assert rel_err(dW, dWr) < (1e-4 if dt == torch.float32 else 2e-3)
+    assert rel_err(db, dC.float().sum(0)) < (1e-4 if dt == torch.float32 else 2e-3)
+
+
+ACTS = [("relu", F.relu), ("hswish", F.hardswish), ("lrelu", lambda t: F.leaky_relu(t, 0.01)), ("none", lambda t: t)]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("act", ACTS, ids=[a[0] for a in ACTS])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_act_dropout_fwd_bwd(act, training, dt):
+    from picklebot_b200 import blocks, ops
+    name, fn = act
+    B, R, C = 3, 77, 40
+    z = (rnd(B, R, C, seed=1) * 2 + 0.5).to(dt).contiguous()
+    gamma, beta = rnd(C, seed=2) + 1.5, rnd(C, seed=3)
+    rm, rv = rnd(C, seed=4), rnd(C, seed=5).abs() + 0.5
+    mask = (torch.empty(B, C).bernoulli_(0.8, generator=torch.Generator().manual_seed(6)) / 0.8).cuda()
+    rm0, rv0 = rm.clone(), rv.clone()
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    out, st = blocks.bn_forward(z.view(-1, C), B, C, gamma, beta, rm, rv, nbt, training, 1e-5, 0.1,
+                                ops.ACT_CODES[name], 0.01, mask)
+    zr = z.float().permute(0, 2, 1).requires_grad_(True)            # (B,C,R)
+    g_r, b_r = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_r, rv_r = rm0.clone(), rv0.clone()
+    ref = fn(F.batch_norm(zr, rm_r, rv_r, g_r, b_r, training, 0.1, 1e-5)) * mask[:, :, None]
+    assert rel_err(out.float().view(B, R, C), ref.permute(0, 2, 1)) < tol(dt)
+    if training:
+        assert rel_err(rm, rm_r) < 1e-5 and rel_err(rv, rv_r) < 1e-5 and int(nbt) == 1
+    dout = rnd(B, R, C, dt=dt, seed=7)
+    ref.backward(dout.float().permute(0, 2, 1))
+    dz, dg, db = ops.bn_act_bwd(dout.view(-1, C), False, z.view(-1, C), *st, mask, B, C, ops.ACT_CODES[name],
+                                training, 0.01)
+    assert rel_err(dz.float().view(B, R, C), zr.grad.permute(0, 2, 1)) < tol(dt)
+    assert rel_err(dg, g_r.grad) < (1e-4 if dt == torch.float32 else 5e-3)
+    assert rel_err(db, b_r.grad) < (1e-4 if dt == torch.float32 else 5e-3)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_bn_bwd_broadcast_dout(dt):
+    """Gradient of a global average pool broadcast over the rows (block6 -> classifier pool)."""
+    from picklebot_b200 import blocks, ops
+    B, R, C = 4, 33, 64
+    z = rnd(B, R, C, dt=dt, seed=1)
+    gamma, beta = rnd(C, seed=2) + 1.5, rnd(C, seed=3)
+    _, st = blocks.bn_forward(z.view(-1, C), B, C, gamma, beta, None, None, None, True, 1e-5, 0.1,
+                              ops.ACT_HSWISH, 0.0, None)
+    dfeat = rnd(B, C, seed=4)
+    zr = z.float().requires_grad_(True)
+    g_r = gamma.clone().requires_grad_(True)
+    a = F.hardswish(F.batch_norm(zr.permute(0, 2, 1), None, None, g_r, beta, True, 0.1, 1e-5))
+    (a.mean(2) * dfeat).sum().backward()
+    dz, dg, _ = ops.bn_act_bwd((dfeat / R).contiguous(), True, z.view(-1, C), *st, None, B, C, ops.ACT_HSWISH, True)
+    assert rel_err(dz.float().view(B, R, C), zr.grad) < tol(dt)
+    assert rel_err(dg, g_r.grad) < (1e-4 if dt == torch.float32 else 5e-3)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_squeeze_excite_pieces(dt):
+    from picklebot_b200 import ops
+    B, R, C, Ch = 3, 50, 72, 18
+    x = rnd(B, R, C, dt=dt, seed=1)
+    W1, b1, W2, b2 = rnd(Ch, C, seed=2, scale=0.4), rnd(Ch, seed=3), rnd(C, Ch, seed=4, scale=0.8), rnd(C, seed=5)
+    pooled = ops.pool_fwd(x, B, C)
+    assert rel_err(pooled, x.float().mean(1)) < 1e-5
+    hidden, gate = ops.se_fc_fwd(pooled, W1, b1, W2, b2)
+    pr = pooled.clone().requires_grad_(True)
+    W1r, b1r, W2r, b2r = [t.clone().requires_grad_(True) for t in (W1, b1, W2, b2)]
+    hr = F.relu(pr @ W1r.t() + b1r)
+    gr = F.hardsigmoid(hr @ W2r.t() + b2r)
+    assert rel_err(hidden, hr) < 1e-5 and rel_err(gate, gr) < 1e-5
+    y = ops.rowscale(x, gate, B, C)
+    assert rel_err(y.float(), x.float() * gate[:, None, :]) < tol(dt)
+    g = rnd(B, R, C, dt=dt, seed=6)
+    dgate = ops.rowdot(g, x, B, C)
+    assert rel_err(dgate, (g.float() * x.float()).sum(1)) < 1e-4
+    gr.backward(dgate)
+    dmean, dW1, db1, dW2, db2 = ops.se_fc_bwd(dgate, pooled, hidden, gate, W1, W2, 1.0 / R)
+    assert rel_err(dmean, pr.grad / R) < 1e-4
+    for mine, ref in ((dW1, W1r.grad), (db1, b1r.grad), (dW2, W2r.grad), (db2, b2r.grad)):
+        assert rel_err(mine, ref) < 1e-4
+    g2 = g.clone()
+    ops.scale_add_(g2, gate, dmean, B, C)
+    assert rel_err(g2.float(), g.float() * gate[:, None, :] + dmean[:, None, :]) < tol(dt)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("src", ["u8_ndhwc", "f32_ncdhw", "act_ndhwc"])
+@pytest.mark.parametrize("conv", [((3, 3, 3), (2, 2, 2), (1, 1, 1), True), ((1, 3, 3), (1, 2, 2), (0, 1, 1), False)],
+                         ids=["mobilenet", "movinet"])
+def test_stem_fwd_wgrad(conv, src, dt):
+    from picklebot_b200 import ops
+    k, s, p, has_bias = conv
+    B, T, H, W = 2, 5, 17, 15
+    g = torch.Generator().manual_seed(1)
+    u8 = torch.randint(0, 256, (B, T, H, W, 3), generator=g, dtype=torch.uint8).cuda()
+    if src == "u8_ndhwc":
+        x = u8.permute(0, 4, 1, 2, 3)                       # raw clip, /255 fused in the kernel
+        xr = (u8.permute(0, 4, 1, 2, 3).to(dt) / 255).float()
+    elif src == "f32_ncdhw":
+        x = (u8.permute(0, 4, 1, 2, 3).float() / 255).contiguous()
+        xr = x.to(dt).float()
+    else:
+        x = u8.permute(0, 4, 1, 2, 3).to(dt) / 255           # exactly train.py:106
+        xr = x.float()
+    w = rnd(16, 3, *k, seed=2, scale=0.3)
+    bias = rnd(16, seed=3) if has_bias else None
+    y = ops.stem_fwd(x, w, bias, k, s, p, dt)
+    wr = w.to(dt).float().requires_grad_(True)
+    br = bias.clone().requires_grad_(True) if has_bias else None
+    yr = F.conv3d(xr, wr, br, s, p)
+    assert rel_err(y.float(), yr.permute(0, 2, 3, 4, 1)) < tol(dt)
+    dy = rnd(*y.shape, dt=dt, seed=4)
+    yr.backward(dy.float().permute(0, 4, 1, 2, 3))
+    dw, db = ops.stem_wgrad(x, dy, w.shape, k, s, p, has_bias)
+    assert rel_err(dw, wr.grad) < (1e-4 if dt == torch.float32 else 2e-3)
+    if has_bias:
+        assert rel_err(db, br.grad) < (1e-4 if dt == torch.float32 else 2e-3)
+
+
+def test_errors_are_loud():
+    from picklebot_b200 import _lib, ops
+    x = torch.zeros(1, 2, 2, 2, 12, device="cuda")           # C=12 is not a multiple of 8
+    w_tc = torch.zeros(9, 12, device="cuda")
+    with pytest.raises(_lib.PicklebotKernelError):
+        ops.dwconv_fwd(x, w_tc, (1, 3, 3), (1, 1, 1), (1, 1, 1))
+    with pytest.raises(RuntimeError):
+        ops.colstats(torch.zeros(4, 8), 8)                    # CPU tensor
+    assert _lib.lib().pb_device_check() == 0
