@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Headline benchmark: MobileNetLarge3D bf16 training clips/s (BASELINE.json config 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one optimiser step over a global batch of 512 synthetic clips (3x16x224x224): every rank runs
+512/(64*N) micro-batches of 64 clips (forward under bf16 autocast, CrossEntropyLoss, backward, DDP's
+bucketed NCCL all-reduce overlapping backward when N>1), then one AdamW step.  Work per step is fixed, so
+scaling is "strong"; the per-GPU micro-batch stays 64 so BatchNorm statistics do not depend on N
+(SURVEY.md section 8d, config 3).
+
+value   clips/s with the uint8 clips already resident in HBM (distinct buffers per micro-batch, 154 MB each,
+        i.e. larger than the 126 MB L2, so no cache flush is needed between iterations).
+e2e     the same step fed from pinned HOST memory through the public module API: per micro-batch H2D copy
+        of the uint8 clip batch + labels (on a side stream, double buffered) and a D2H read of the loss.
+roofline  per-kernel-family GB/s from CUDA events recorded around every C-ABI launch on the launching
+        stream (separate instrumented steps after the timed region), against MEASURED_PEAKS.json.
+cpu_baseline  the oracle (a restatement of the reference's torch ops; the reference itself cannot travel
+        to the GPU box) running the same train step on the host cores on a bounded sample.
+
+--impl reference times that CPU path alone (rank 0; other ranks exit 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+MODEL = "MobileNetLarge3D"
+NUM_CLASSES = 2
+GLOBAL_BATCH = 512
+MICRO = 64
+CLIP = (16, 224, 224)
+METRIC = "MobileNetLarge3D train clips/s"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--micro", type=int, default=MICRO)
+    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=1)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's train step on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_train_clips_per_s(batch, reps, warm=1):
+    from oracle import picklebot_oracle as O          # bench's cpu_baseline / reference leg only
+    import picklebot_b200 as pb
+    from picklebot_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd0 = synth.synthetic_state_dict(pb.MobileNetLarge3D(num_classes=NUM_CLASSES).state_dict())
+    clips = synth.synthetic_clips_u8(batch, *CLIP, seed=0)
+    x = synth.clips_to_features(clips, torch.float32).contiguous()
+    labels = synth.synthetic_labels(batch, NUM_CLASSES)
+    times = []
+    for i in range(warm + reps):
+        sd = O.clone_state(sd0, requires_grad=True)
+        t0 = time.perf_counter()
+        torch.manual_seed(7)
+        O.train_step(MODEL, sd, x, labels)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return batch / min(times), batch / (sum(times) / len(times)), times
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    batch = 4
+    t0 = time.perf_counter()
+    best, mean, times = cpu_train_clips_per_s(batch, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
+    value = mean
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * batch / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MobileNetLarge3D train step (fwd+CE+bwd), 3x16x224x224 clips, CPU fp32",
+                   "global_batch": args.global_batch, "micro_batch": batch, "clip": list(CLIP)},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{len(times)} train steps of {batch} clips each (one step = a bounded sample "
+                                   f"of the {args.global_batch}-clip global batch); oracle = torch-op restatement "
+                                   f"of the reference, which is pure Python and absent on the GPU box"},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch.distributed as dist
+    import picklebot_b200 as pb
+    from picklebot_b200 import _lib, synth
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    assert _lib.lib().pb_device_check() == 0, _lib.lib().pb_last_error_string().decode()
+    micro = args.micro
+    assert args.global_batch % (micro * world) == 0
+    accum = args.global_batch // (micro * world)
+
+    torch.manual_seed(1234)
+    model = pb.MobileNetLarge3D(num_classes=NUM_CLASSES)
+    model.load_state_dict(synth.synthetic_state_dict(model.state_dict()))
+    model = model.to(dev).train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=5e-4, fused=True)
+
+    # synthetic uint8 clips: this rank's shard of each global batch, distinct per micro-batch
+    clips = [synth.synthetic_clips_u8_device(micro, *CLIP, seed=1000 * rank + a, device=dev) for a in range(accum)]
+    labels = [synth.synthetic_labels(micro, NUM_CLASSES, seed=77 + 1000 * rank + a).to(dev) for a in range(accum)]
+    loss_buf = torch.zeros((), device=dev)
+
+    def micro_step(x_u8, y, sync_grads):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = net(x_u8.permute(0, 4, 1, 2, 3))        # (B,3,T,H,W) view of the uint8 NTHWC batch
+            loss = F.cross_entropy(logits.float(), y) / accum
+        if world > 1 and not sync_grads:
+            with net.no_sync():
+                loss.backward()
+        else:
+            loss.backward()
+        return loss.detach()
+
+    def step_resident():
+        tot = None
+        for a in range(accum):
+            l = micro_step(clips[a], labels[a], a == accum - 1)
+            tot = l if tot is None else tot + l
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return tot
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = args.global_batch / (ms_per_step / 1000.0)
+
+    # ---- end to end: pinned host clips -> H2D (side stream, double buffered) -> step -> D2H loss ----
+    e2e = None
+    if not args.no_e2e:
+        host_clips = [c.cpu().pin_memory() for c in clips]
+        host_labels = [l.cpu().pin_memory() for l in labels]
+        copy_stream = torch.cuda.Stream(device=dev)
+        dbuf = [torch.empty_like(clips[0]) for _ in range(2)]
+        lbuf = [torch.empty_like(labels[0]) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+
+        def upload(a, slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                dbuf[slot].copy_(host_clips[a], non_blocking=True)
+                lbuf[slot].copy_(host_labels[a], non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def step_e2e():
+            cur = torch.cuda.current_stream()
+            upload(0, 0)
+            tot = None
+            for a in range(accum):
+                slot = a & 1
+                if a + 1 < accum:
+                    upload(a + 1, (a + 1) & 1)
+                cur.wait_event(ready[slot])
+                l = micro_step(dbuf[slot], lbuf[slot], a == accum - 1)
+                consumed[slot].record(cur)
+                tot = l if tot is None else tot + l
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            host_loss.copy_(tot, non_blocking=True)
+            torch.cuda.current_stream().synchronize()          # the user reads the loss every step
+            return float(host_loss)
+
+        for s in range(2):
+            consumed[s].record(torch.cuda.current_stream())
+        step_e2e()
+        ms_e = timed(step_e2e, args.steps) / args.steps
+        e2e = {"value": args.global_batch / (ms_e / 1000.0), "unit": "clips/s",
+               "h2d_bytes_per_step": accum * (clips[0].numel() + labels[0].numel() * 8),
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e}
+        del host_clips, dbuf
+
+    # ---- per-kernel roofline: instrumented steps (CUDA events around every launch) -----------------
+    peak, peak_kind = peaks()
+    kernels, roofline = {}, None
+    if rank == 0 or world > 1:
+        prof = _lib.KernelProfiler()
+        _lib.PROFILER = prof
+        for _ in range(max(1, args.profile_steps)):
+            step_resident()
+        _lib.PROFILER = None
+        summ = prof.summary()
+        tot_ms = sum(v["ms"] for v in summ.values())
+        for name, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"]):
+            gbs = v["bytes"] / (v["ms"] * 1e6) if v["ms"] > 0 else 0.0
+            kernels[name] = {"launches_per_step": v["launches"] // max(1, args.profile_steps),
+                             "ms_per_step": v["ms"] / max(1, args.profile_steps), "share": v["ms"] / tot_ms,
+                             "GBps": gbs, "frac_of_hbm_peak": gbs / peak,
+                             "avg_us": 1000.0 * v["ms"] / v["launches"],
+                             "alg_bytes_per_launch": v["bytes"] / v["launches"]}
+        top = next(iter(kernels))
+        kt = kernels[top]
+        roofline = {"kernel": top, "bound": "hbm", "achieved": kt["GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": kt["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_kind + " copy bandwidth",
+                    "share_of_step": kt["share"], "avg_launch_us": kt["avg_us"],
+                    "alg_bytes_per_launch": kt["alg_bytes_per_launch"]}
+        dw = {k: v for k, v in kernels.items() if k.startswith("pb_dwconv3d")}
+        if dw:
+            b = sum(v["GBps"] * v["ms_per_step"] for v in dw.values())
+            t = sum(v["ms_per_step"] for v in dw.values())
+            roofline["depthwise_conv3d_GBps"] = b / t
+            roofline["depthwise_conv3d_frac"] = b / t / peak
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        best, mean, times = cpu_train_clips_per_s(4, reps=3, warm=1)
+        cpu = {"value": mean, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{len(times)} train steps (fwd+CE+bwd) of 4 clips 3x16x224x224, fp32, oracle "
+                         f"(torch-op restatement of the reference) on the host cores"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "MobileNetLarge3D training step, bf16 autocast, synthetic uint8 clips 3x16x224x224 "
+                                   "(BASELINE.json configs[2])",
+                       "global_batch": args.global_batch, "micro_batch_per_gpu": micro, "accum_steps": accum,
+                       "parallelism": f"dp{world}", "optimizer": "torch.optim.AdamW(fused=True) inside the timed region",
+                       "l2": "inputs larger than L2 (154 MB uint8 per micro-batch, distinct buffers); no flush",
+                       "num_classes": NUM_CLASSES},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "kernels": kernels,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

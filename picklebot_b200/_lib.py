@@ -81,11 +81,43 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
-def call(name: str, *args) -> None:
+class KernelProfiler:
+    """Optional per-launch timing: CUDA events recorded on the launching (current torch) stream around
+    every C-ABI call, with the algorithmic bytes the caller attributes to it.  Used by bench.py for the
+    live roofline numbers; off (None) by default so the hot path pays nothing."""
+
+    def __init__(self):
+        self.records = []          # (name, start_event, end_event, algorithmic_bytes)
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, nbytes in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += nbytes
+        return out
+
+
+PROFILER = None
+
+
+def call(name: str, *args, nbytes: int = 0) -> None:
+    prof = PROFILER
+    if prof is not None:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib(), name)(*args)
     if rc != PB_OK:
         msg = lib().pb_last_error_string()
         raise PicklebotKernelError(f"{name} failed (code {rc}): {msg.decode() if msg else '?'}")
+    if prof is not None:
+        e1.record()
+        prof.records.append((name, e0, e1, nbytes))
 
 
 def launch_count() -> int:

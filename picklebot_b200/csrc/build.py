@@ -20,7 +20,7 @@ SOURCES = ["runtime.cu", "dwconv.cu", "dwconv_tiled.cu", "pwgemm_simt.cu", "pwge
            "se_pool.cu", "stem.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v" if "--verbose" in sys.argv else "-O3"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v" if "--verbose" in sys.argv else "-O3"]
 
 
 def _deps():

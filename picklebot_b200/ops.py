@@ -13,7 +13,11 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_HSIGMOID, ACT_HSWISH, ACT_LRELU, ACT_NONE, ACT_RELU, PB_BF16, PB_F32, PB_F32_RBF16,
-                   PB_U8, call)
+                   PB_U8)
+
+
+def call(name, *args, nbytes=0):
+    _lib.call(name, *args, nbytes=nbytes)
 
 ACT_CODES = {"none": ACT_NONE, "relu": ACT_RELU, "hswish": ACT_HSWISH, "lrelu": ACT_LRELU,
              "hsigmoid": ACT_HSIGMOID}
@@ -110,7 +114,8 @@ def dwconv_fwd(x: torch.Tensor, w_tc: torch.Tensor, k, s, p) -> torch.Tensor:
     _chk(x, "dwconv_fwd.x")
     d = _dw_dims(x.shape, k, s, p)
     y = torch.empty((d[0], d[14], d[15], d[16], d[1]), dtype=x.dtype, device=x.device)
-    call("pb_dwconv3d_fwd", x.data_ptr(), w_tc.data_ptr(), y.data_ptr(), _dt(x), *d, _st())
+    call("pb_dwconv3d_fwd", x.data_ptr(), w_tc.data_ptr(), y.data_ptr(), _dt(x), *d, _st(),
+         nbytes=(x.numel() + y.numel()) * x.element_size() + w_tc.numel() * x.element_size())
     return y
 
 
@@ -118,7 +123,8 @@ def dwconv_dgrad(dy: torch.Tensor, w_tc: torch.Tensor, x_shape, k, s, p) -> torc
     _chk(dy, "dwconv_dgrad.dy")
     d = _dw_dims(x_shape, k, s, p)
     dx = torch.empty(tuple(x_shape), dtype=dy.dtype, device=dy.device)
-    call("pb_dwconv3d_dgrad", dy.data_ptr(), w_tc.data_ptr(), dx.data_ptr(), _dt(dy), *d, _st())
+    call("pb_dwconv3d_dgrad", dy.data_ptr(), w_tc.data_ptr(), dx.data_ptr(), _dt(dy), *d, _st(),
+         nbytes=(dx.numel() + dy.numel()) * dy.element_size() + w_tc.numel() * dy.element_size())
     return dx
 
 
@@ -127,7 +133,8 @@ def dwconv_wgrad(x: torch.Tensor, dy: torch.Tensor, k, s, p) -> torch.Tensor:
     _chk(x, "dwconv_wgrad.x"); _chk(dy, "dwconv_wgrad.dy")
     d = _dw_dims(x.shape, k, s, p)
     dw_tc = torch.empty((k[0] * k[1] * k[2], x.shape[-1]), dtype=torch.float32, device=x.device)
-    call("pb_dwconv3d_wgrad", x.data_ptr(), dy.data_ptr(), dw_tc.data_ptr(), _dt(x), *d, _st())
+    call("pb_dwconv3d_wgrad", x.data_ptr(), dy.data_ptr(), dw_tc.data_ptr(), _dt(x), *d, _st(),
+         nbytes=(x.numel() + dy.numel()) * x.element_size() + dw_tc.numel() * 4)
     return dw_tc
 
 
@@ -166,7 +173,8 @@ def gemm_simt(A: torch.Tensor, W: torch.Tensor, N: int, K: int, w_sn: int, w_sk:
     R = rows // Bt
     C = torch.empty((rows, N), dtype=A.dtype, device=A.device)
     call("pb_pw_gemm_simt", A.data_ptr(), W.data_ptr(), w_sn, w_sk, _p(bias), _p(ascale), _p(colscale),
-         _p(coladd), C.data_ptr(), _dt(A), Bt, R, K, N, _st())
+         _p(coladd), C.data_ptr(), _dt(A), Bt, R, K, N, _st(),
+         nbytes=(A.numel() + C.numel() + N * K) * A.element_size())
     return C
 
 
@@ -177,7 +185,8 @@ def wgrad_simt(A: torch.Tensor, dC: torch.Tensor, K: int, N: int, ascale=None, B
     R = rows // Bt
     dW = torch.empty((N, K), dtype=torch.float32, device=A.device)
     db = torch.empty((N,), dtype=torch.float32, device=A.device) if want_bias else None
-    call("pb_pw_wgrad_simt", A.data_ptr(), dC.data_ptr(), _p(ascale), dW.data_ptr(), _p(db), _dt(A), Bt, R, K, N, _st())
+    call("pb_pw_wgrad_simt", A.data_ptr(), dC.data_ptr(), _p(ascale), dW.data_ptr(), _p(db), _dt(A), Bt, R, K, N, _st(),
+         nbytes=(A.numel() + dC.numel()) * A.element_size() + N * K * 4)
     return dW, db
 
 
@@ -188,7 +197,7 @@ def colstats(x: torch.Tensor, C: int) -> torch.Tensor:
     _chk(x, "colstats.x")
     M = x.numel() // C
     sums = torch.empty((2, C), dtype=torch.float64, device=x.device)
-    call("pb_colstats", x.data_ptr(), _dt(x), M, C, sums.data_ptr(), _st())
+    call("pb_colstats", x.data_ptr(), _dt(x), M, C, sums.data_ptr(), _st(), nbytes=x.numel() * x.element_size())
     return sums
 
 
@@ -205,7 +214,7 @@ def bn_act_fwd(z: torch.Tensor, scale, shift, mask, B: int, C: int, act: int, sl
     R = z.numel() // (B * C)
     out = torch.empty_like(z)
     call("pb_bn_act_fwd", z.data_ptr(), scale.data_ptr(), shift.data_ptr(), _p(mask), out.data_ptr(), _dt(z),
-         B, R, C, act, slope, _st())
+         B, R, C, act, slope, _st(), nbytes=2 * z.numel() * z.element_size())
     return out
 
 
@@ -218,14 +227,15 @@ def bn_act_bwd(dout: torch.Tensor, dout_bcast: bool, z: torch.Tensor, scale, shi
     dev = z.device
     sums = torch.empty((2, C), dtype=torch.float64, device=dev)
     call("pb_bn_act_bwd_reduce", dout.data_ptr(), int(dout_bcast), z.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-         mean.data_ptr(), invstd.data_ptr(), _p(mask), sums.data_ptr(), _dt(z), B, R, C, act, slope, _st())
+         mean.data_ptr(), invstd.data_ptr(), _p(mask), sums.data_ptr(), _dt(z), B, R, C, act, slope, _st(),
+         nbytes=(z.numel() + (0 if dout_bcast else dout.numel())) * z.element_size())
     small = torch.empty((4, C), dtype=torch.float32, device=dev)   # dgamma | dbeta | coef0 | coef1
     call("pb_bn_bwd_finalize", sums.data_ptr(), M, int(training), small[0].data_ptr(), small[1].data_ptr(),
          small[2].data_ptr(), C, _st())
     dz = torch.empty_like(z)
     call("pb_bn_act_bwd_apply", dout.data_ptr(), int(dout_bcast), z.data_ptr(), scale.data_ptr(), shift.data_ptr(),
          mean.data_ptr(), invstd.data_ptr(), _p(mask), small[2].data_ptr(), dz.data_ptr(), _dt(z), B, R, C, act,
-         slope, _st())
+         slope, _st(), nbytes=(2 * z.numel() + (0 if dout_bcast else dout.numel())) * z.element_size())
     return dz, small[0], small[1]
 
 
@@ -236,7 +246,7 @@ def pool_fwd(x: torch.Tensor, B: int, C: int) -> torch.Tensor:
     _chk(x, "pool_fwd.x")
     R = x.numel() // (B * C)
     mean = torch.empty((B, C), dtype=torch.float32, device=x.device)
-    call("pb_pool_fwd", x.data_ptr(), _dt(x), B, R, C, mean.data_ptr(), _st())
+    call("pb_pool_fwd", x.data_ptr(), _dt(x), B, R, C, mean.data_ptr(), _st(), nbytes=x.numel() * x.element_size())
     return mean
 
 
@@ -270,7 +280,8 @@ def rowscale(x: torch.Tensor, gate: torch.Tensor, B: int, C: int) -> torch.Tenso
     _chk(x, "rowscale.x")
     R = x.numel() // (B * C)
     y = torch.empty_like(x)
-    call("pb_rowscale", x.data_ptr(), gate.data_ptr(), y.data_ptr(), _dt(x), B, R, C, _st())
+    call("pb_rowscale", x.data_ptr(), gate.data_ptr(), y.data_ptr(), _dt(x), B, R, C, _st(),
+         nbytes=2 * x.numel() * x.element_size())
     return y
 
 
@@ -278,14 +289,16 @@ def rowdot(g: torch.Tensor, y: torch.Tensor, B: int, C: int) -> torch.Tensor:
     _chk(g, "rowdot.g"); _chk(y, "rowdot.y")
     R = g.numel() // (B * C)
     out = torch.empty((B, C), dtype=torch.float32, device=g.device)
-    call("pb_rowdot", g.data_ptr(), y.data_ptr(), _dt(g), B, R, C, out.data_ptr(), _st())
+    call("pb_rowdot", g.data_ptr(), y.data_ptr(), _dt(g), B, R, C, out.data_ptr(), _st(),
+         nbytes=2 * g.numel() * g.element_size())
     return out
 
 
 def scale_add_(g: torch.Tensor, gate: torch.Tensor, add: torch.Tensor, B: int, C: int) -> torch.Tensor:
     _chk(g, "scale_add.g")
     R = g.numel() // (B * C)
-    call("pb_scale_add", g.data_ptr(), gate.data_ptr(), add.data_ptr(), _dt(g), B, R, C, _st())
+    call("pb_scale_add", g.data_ptr(), gate.data_ptr(), add.data_ptr(), _dt(g), B, R, C, _st(),
+         nbytes=2 * g.numel() * g.element_size())
     return g
 
 
@@ -307,7 +320,7 @@ def stem_fwd(x: torch.Tensor, w: torch.Tensor, bias, k, s, p, out_dtype: torch.d
     strides, dims, oshape = _stem_args(x, k, s, p, w.shape[0])
     y = torch.empty(oshape, dtype=out_dtype, device=x.device)
     call("pb_stem_conv_fwd", x.data_ptr(), _dt(x), *strides, 255.0, w.data_ptr(), _p(bias), y.data_ptr(), _dt(y),
-         *dims, _st())
+         *dims, _st(), nbytes=x.numel() * x.element_size() + y.numel() * y.element_size())
     return y
 
 
@@ -317,5 +330,5 @@ def stem_wgrad(x: torch.Tensor, dy: torch.Tensor, w_shape, k, s, p, want_bias: b
     dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
     db = torch.empty((w_shape[0],), dtype=torch.float32, device=x.device) if want_bias else None
     call("pb_stem_conv_wgrad", x.data_ptr(), _dt(x), *strides, 255.0, dy.data_ptr(), _dt(dy), dw.data_ptr(), _p(db),
-         *dims, _st())
+         *dims, _st(), nbytes=x.numel() * x.element_size() + dy.numel() * dy.element_size())
     return dw, db

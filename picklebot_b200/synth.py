@@ -58,6 +58,33 @@ def synthetic_clips_u8(batch: int, frames: int = 16, height: int = 224, width: i
     return img.to(device)
 
 
+def synthetic_clips_u8_device(batch: int, frames: int, height: int, width: int, seed: int,
+                               device: str | torch.device) -> torch.Tensor:
+    """Same clip family as ``synthetic_clips_u8`` but built with int32 math on ``device`` (bench-sized
+    batches: 64 clips are 154 MB of uint8).  Per-clip parameters still come from the CPU generator; only
+    the pixel noise uses the device generator, so these clips are not bit-identical to the CPU ones."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    B, T, H, W = batch, frames, height, width
+    i32 = dict(dtype=torch.int32, device=device)
+    bg = torch.randint(30, 200, (B, 1, 1, 1, 3), generator=g).to(**i32)
+    fg = torch.randint(0, 256, (B, 1, 1, 1, 3), generator=g).to(**i32)
+    cx0 = torch.randint(0, W, (B, 1, 1, 1), generator=g).to(**i32)
+    cy0 = torch.randint(0, H, (B, 1, 1, 1), generator=g).to(**i32)
+    vx = torch.randint(-6, 7, (B, 1, 1, 1), generator=g).to(**i32)
+    vy = torch.randint(-6, 7, (B, 1, 1, 1), generator=g).to(**i32)
+    rad = torch.randint(max(4, H // 28), max(6, H // 9), (B, 1, 1, 1), generator=g).to(**i32)
+    t = torch.arange(T, **i32).view(1, T, 1, 1)
+    ys = torch.arange(H, **i32).view(1, 1, H, 1)
+    xs = torch.arange(W, **i32).view(1, 1, 1, W)
+    d2 = (xs - (cx0 + vx * t)) ** 2 + (ys - (cy0 + vy * t)) ** 2
+    r2 = rad * rad
+    bump = (torch.clamp(r2 - d2, min=0) * 256 // r2).unsqueeze(-1)
+    img = bg + (fg - bg) * bump // 256
+    gd = torch.Generator(device=device).manual_seed(seed)
+    noise = torch.randint(0, 13, (B, T, H, W, 3), generator=gd, dtype=torch.int32, device=device)
+    return torch.clamp(img + noise - 6, 0, 255).to(torch.uint8)
+
+
 def clips_to_features(clips_u8: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """The reference's ``extract_features_labels`` (train.py:102-108): a ``(B,C,T,H,W)`` view with
     channels-last-3d strides, cast and divided by 255 (same op order, so bf16 values match)."""
