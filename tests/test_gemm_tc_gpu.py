@@ -1,0 +1,59 @@
+"""tcgen05/TMEM/TMA GEMM against fp32 torch matmul on the bf16-rounded operands (B200 only)."""
+import pytest
+import torch
+
+from _util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return ((torch.rand(*shape, generator=g) * 2 - 1) * scale).cuda()
+
+
+# (Bt, R, K, N): pointwise layers of the three models, ragged row counts, K tails, N > 256
+CASES = [(1, 128, 64, 16), (1, 1000, 16, 16), (1, 5000, 16, 64), (1, 777, 24, 72), (2, 931, 960, 160),
+         (3, 200, 672, 112), (1, 3000, 160, 960), (1, 1234, 112, 672), (4, 37, 72, 40), (1, 4096, 184, 80),
+         (2, 300, 80, 184), (1, 50000, 40, 240), (1, 129, 8, 8), (64, 735, 960, 160)]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_gemm_tc_plain_and_epilogue(case):
+    from picklebot_b200 import gemm_tc
+    Bt, R, K, N = case
+    A = rnd(Bt * R, K, seed=1).bfloat16()
+    W = rnd(N, K, seed=2, scale=0.3).bfloat16()
+    C = gemm_tc.gemm(A, W, N, K)
+    ref = A.float() @ W.float().t()
+    assert rel_err(C.float(), ref) < 6e-3
+    bias, cs, ca = rnd(N, seed=3), rnd(Bt, N, seed=4), rnd(Bt, N, seed=5)
+    C2 = gemm_tc.gemm(A, W, N, K, Bw=1, Bt=Bt, bias=bias, colscale=cs, coladd=ca)
+    ref2 = ((ref + bias).view(Bt, R, N) * cs[:, None, :] + ca[:, None, :]).view(-1, N)
+    assert rel_err(C2.float(), ref2) < 6e-3
+
+
+@pytest.mark.parametrize("case", [(2, 931, 960, 160), (3, 200, 672, 112), (4, 37, 72, 40), (64, 49, 576, 96)])
+def test_gemm_tc_per_sample_weights(case):
+    """squeeze-excite gate folded into per-sample weights (pb_fold_gate_bf16)."""
+    from picklebot_b200 import gemm_tc, ops
+    Bt, R, K, N = case
+    A = rnd(Bt * R, K, seed=1).bfloat16()
+    W = rnd(N, K, seed=2, scale=0.3)
+    gate = rnd(Bt, K, seed=3).abs() + 0.1
+    Wb = ops.fold_gate(W, gate)
+    assert rel_err(Wb.float(), W[None] * gate[:, None, :]) < 4e-3
+    C = gemm_tc.gemm(A, Wb, N, K, Bw=Bt, Bt=Bt)
+    ref = torch.einsum("brk,bnk->brn", A.float().view(Bt, R, K), Wb.float()).reshape(-1, N)
+    assert rel_err(C.float(), ref) < 6e-3
+
+
+def test_gemm_tc_matches_simt_bitwise_scale():
+    """Same operands through the CUDA-core kernel: both accumulate in fp32, so they agree to bf16 round-off."""
+    from picklebot_b200 import gemm_tc, ops
+    R, K, N = 2000, 120, 40
+    A = rnd(R, K, seed=1).bfloat16()
+    W = rnd(N, K, seed=2, scale=0.3)
+    a = gemm_tc.gemm(A, W.bfloat16(), N, K)
+    b = ops.gemm_simt(A, W, N, K, K, 1)
+    assert rel_err(a.float(), b.float()) < 3e-3
