@@ -95,8 +95,15 @@ int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const float* bias,
  * Optionally also dbias[n] = sum dC (NULL to skip). */
 int pb_pw_wgrad_simt(const void* A, const void* dC, const float* ascale, float* dW, float* dbias,
                      int dtype, int Bt, long long R, int K, int N, pb_stream_t stream);
-int pb_pw_wgrad_tc(const void* A, const void* dC, float* dW_partial, float* dW,
-                   int Bt, long long R, int K, int N, int per_batch, pb_stream_t stream);
+/* tcgen05 weight gradient for bf16 activations (both operands are MN-major shared-memory tiles fed by TMA).
+ *   dW[n][k]    = sum_b gate[b][k] * P_b[n][k],   P_b[n][k] = sum_r dC[b][r][n] * A[b][r][k]
+ *   dgate[b][k] = sum_n Wf32[n][k] * P_b[n][k]   (the squeeze-excite gate gradient, for free: no extra
+ *                 pass over the expanded activations)
+ * gate, Wf32 and dgate are optional (all NULL: plain wgrad; pass Bt = 1, R = total rows then).
+ * workspace: pb_pw_wgrad_tc_workspace_bytes(Bt,R,K,N) bytes of caller-owned scratch. */
+long long pb_pw_wgrad_tc_workspace_bytes(int Bt, long long R, int K, int N);
+int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, const float* Wf32, void* workspace,
+                   float* dW, float* dgate, int Bt, long long R, int K, int N, pb_stream_t stream);
 
 /* fp32 [rows][cols] -> dst (dtype) [cols][rows] if transpose else [rows][cols]. */
 int pb_cast_matrix(const float* src, void* dst, int dst_dtype, int rows, int cols, int transpose,

@@ -28,7 +28,7 @@ SIGNATURES = {
     "pb_pw_gemm_simt": "ppllpppppiiliip",
     "pb_pw_gemm_tc": "ppipppp" + "iliip",
     "pb_pw_wgrad_simt": "pppppiiliip",
-    "pb_pw_wgrad_tc": "ppppiliiip",
+    "pb_pw_wgrad_tc": "pppppppiliip",
     "pb_cast_matrix": "ppiiiip",
     "pb_fold_gate_bf16": "pppiiip",
     "pb_colstats": "pilipp",
@@ -46,7 +46,8 @@ SIGNATURES = {
     "pb_stem_conv_fwd": "pi" + "lllll" + "f" + "pppi" + "i" * 18 + "p",
     "pb_stem_conv_wgrad": "pi" + "lllll" + "f" + "pipp" + "i" * 18 + "p",
 }
-PLAIN = ("pb_abi_version", "pb_last_error_string", "pb_launch_count", "pb_device_check")
+PLAIN = ("pb_abi_version", "pb_last_error_string", "pb_launch_count", "pb_device_check",
+         "pb_pw_wgrad_tc_workspace_bytes")
 EXPORTS = tuple(SIGNATURES) + PLAIN
 
 
@@ -68,6 +69,8 @@ def _load() -> ctypes.CDLL:
     lib.pb_last_error_string.restype = ctypes.c_char_p
     lib.pb_launch_count.restype = _L
     lib.pb_device_check.restype = _I
+    lib.pb_pw_wgrad_tc_workspace_bytes.argtypes = [_I, _L, _I, _I]
+    lib.pb_pw_wgrad_tc_workspace_bytes.restype = _L
     return lib
 
 

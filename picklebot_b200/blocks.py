@@ -15,6 +15,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import ops
+from . import gemm_tc          # noqa: F401  (import enables the tcgen05 GEMM path)
 from .ops import ACT_CODES
 
 
@@ -98,7 +99,6 @@ def pw_fwd(A: torch.Tensor, w: torch.Tensor, cache: WeightCache, key: str, bias=
     W = _w2d(w)
     N, K = W.shape
     if ops.use_tc(A.dtype, K, N):
-        from . import gemm_tc
         if gate is not None:
             Wb = ops.fold_gate(W, gate)
             return gemm_tc.gemm(A, Wb, N, K, Bw=Bt, Bt=Bt, bias=bias)
@@ -112,7 +112,6 @@ def pw_dgrad(dC: torch.Tensor, w: torch.Tensor, cache: WeightCache, key: str) ->
     W = _w2d(w)
     N, K = W.shape
     if ops.use_tc(dC.dtype, N, K):
-        from . import gemm_tc
         Wt = cache.get((key, "bf16_t"), w, lambda: ops.cast_matrix(W, N, K, torch.bfloat16, transpose=True))
         return gemm_tc.gemm(dC, Wt, K, N, Bw=1, Bt=1)
     return ops.gemm_simt(dC, W, K, N, 1, K)
@@ -121,12 +120,36 @@ def pw_dgrad(dC: torch.Tensor, w: torch.Tensor, cache: WeightCache, key: str) ->
 def pw_wgrad(A: torch.Tensor, dC: torch.Tensor, w: torch.Tensor, gate=None, Bt: int = 1, want_bias: bool = False):
     W = _w2d(w)
     N, K = W.shape
-    if ops.use_tc(A.dtype, K, N) and gate is None and not want_bias:
-        from . import gemm_tc
-        if gemm_tc.wgrad_ready():
-            return gemm_tc.wgrad(A, dC, K, N).view(w.shape), None
+    if ops.use_tc(A.dtype, K, N) and gemm_tc.wgrad_ready():
+        dW, _ = gemm_tc.wgrad(A, dC, K, N, gate=gate, Bt=Bt)
+        db = ops.colstats(dC, N)[0].float() if want_bias else None
+        return dW.view(w.shape), db
     dW, db = ops.wgrad_simt(A, dC, K, N, ascale=gate, Bt=Bt, want_bias=want_bias)
     return dW.view(w.shape), db
+
+
+def se_pw2_backward(dz: torch.Tensor, y2: torch.Tensor, w2: torch.Tensor, cache: WeightCache, gate, pooled, hidden,
+                    se_w1, se_w2, B: int, R_out: int):
+    """Backward of  z = (y2 * gate) W2^T  with gate = SE(mean(y2)):  returns (dW2, dy2, SE parameter grads).
+    tcgen05 path: the per-sample products P_b = dz_b^T y2_b give dW2 AND dgate, and the input-gradient GEMM
+    applies gate / adds dmean in its epilogue, so y2 and g are each touched once."""
+    W = _w2d(w2)
+    Cout, Cexp = W.shape
+    if ops.use_tc(dz.dtype, Cexp, Cout) and gemm_tc.wgrad_ready():
+        dW2, dgate = gemm_tc.wgrad(y2.view(-1, Cexp), dz, Cexp, Cout, gate=gate, W=W.contiguous(), Bt=B,
+                                   want_dgate=True)
+        dmean, dW1s, db1s, dW2s, db2s = ops.se_fc_bwd(dgate, pooled, hidden, gate, _w2d(se_w1), _w2d(se_w2),
+                                                      1.0 / float(R_out))
+        Wt = cache.get(("w2", "bf16_t"), w2, lambda: ops.cast_matrix(W, Cout, Cexp, torch.bfloat16, transpose=True))
+        dy2 = gemm_tc.gemm(dz, Wt, Cexp, Cout, Bw=1, Bt=B, colscale=gate, coladd=dmean)
+    else:
+        dW2, _ = ops.wgrad_simt(y2.view(-1, Cexp), dz, Cexp, Cout, ascale=gate, Bt=B)
+        g = ops.gemm_simt(dz, W, Cexp, Cout, 1, Cexp)
+        dgate = ops.rowdot(g, y2, B, Cexp)
+        dmean, dW1s, db1s, dW2s, db2s = ops.se_fc_bwd(dgate, pooled, hidden, gate, _w2d(se_w1), _w2d(se_w2),
+                                                      1.0 / float(R_out))
+        dy2 = ops.scale_add_(g, gate, dmean, B, Cexp)
+    return dW2.view(w2.shape), dy2, (dW1s.view(se_w1.shape), db1s, dW2s.view(se_w2.shape), db2s)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -186,16 +209,13 @@ class BottleneckFn(torch.autograd.Function):
             d5 = d5.to(z.dtype)
         dz, dgamma, dbeta = ops.bn_act_bwd(d5, False, z, scale, shift, mean, invstd, mask, B, Cout, cfg.act,
                                            ctx.training, cfg.slope)
-        dw2, _ = pw_wgrad(y2.view(-1, Cexp), dz, w2, gate=gate, Bt=B if gate is not None else 1)
-        g = pw_dgrad(dz, w2, cache, "w2")                       # d(y2 * gate)  [M'][Cexp]
         dse = (None, None, None, None)
         if cfg.use_se:
-            dgate = ops.rowdot(g, y2, B, Cexp)
-            dmean, dW1, db1, dW2, db2 = ops.se_fc_bwd(dgate, pooled, hidden, gate, _w2d(se_w1), _w2d(se_w2),
-                                                      1.0 / float(To * Ho * Wo))
-            ops.scale_add_(g, gate, dmean, B, Cexp)             # dy2 = g*gate + dmean/R
-            dse = (dW1.view(se_w1.shape), db1, dW2.view(se_w2.shape), db2)
-        dy2 = g.view(B, To, Ho, Wo, Cexp)
+            dw2, dy2, dse = se_pw2_backward(dz, y2, w2, cache, gate, pooled, hidden, se_w1, se_w2, B, To * Ho * Wo)
+        else:
+            dw2, _ = pw_wgrad(y2.view(-1, Cexp), dz, w2)
+            dy2 = pw_dgrad(dz, w2, cache, "w2")
+        dy2 = dy2.view(B, To, Ho, Wo, Cexp)
         dwdw_tc = ops.dwconv_wgrad(y1, dy2, cfg.k, cfg.s, cfg.p)
         dwdw = ops.dw_weight_grad_from_tapmajor(dwdw_tc, wdw.shape)
         dy1 = ops.dwconv_dgrad(dy2, wdw_tc, y1.shape, cfg.k, cfg.s, cfg.p)

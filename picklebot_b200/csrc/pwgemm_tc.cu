@@ -233,7 +233,3 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     return PB_OK;
 }
 
-extern "C" int pb_pw_wgrad_tc(const void*, const void*, float*, float*, int, long long, int, int, int, pb_stream_t) {
-    set_error("pw_wgrad_tc: not built in this revision");
-    return PB_ERR_UNSUPPORTED;
-}

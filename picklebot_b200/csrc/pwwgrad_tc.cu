@@ -1,0 +1,264 @@
+// Pointwise-conv weight gradient on tcgen05:  P[n][k] = sum_m dC[m][n] * A[m][k]  (fp32 in TMEM).
+//
+// The reduction runs over the rows m (up to 6.4 M), the output is tiny (N x K <= 960 x 160), so both MMA
+// operands are "MN-major": the row-major activations dC[m][n] and A[m][k] are exactly the transposes the MMA
+// needs, fetched by TMA as 64-row x 128-byte boxes (no transposes in HBM).  One CTA owns one group of
+// output tiles (up to 512 TMEM columns = 128 x 512 accumulators) and one chunk of rows; it streams its rows
+// once through a 3-stage TMA ring, then dumps the fp32 accumulators to a workspace slice.  A second,
+// small kernel sums the slices and, for squeeze-excite blocks, applies the gate per sample and produces
+// the gate gradient from the same per-sample products (so the backward pass never re-reads the expanded
+// activations for it):
+//     dW[n][k]    = sum_b gate[b][k] * P_b[n][k]
+//     dgate[b][k] = sum_n W[n][k]    * P_b[n][k]
+// Replaces the weight-gradient half of nn.Conv3d(kernel_size=1) autograd (train.py:269).
+#include <algorithm>
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace pb {
+namespace tc {
+
+constexpr int WG_ROWS = 64;                 // rows (reduction) per pipeline stage
+constexpr int WG_BOX_BYTES = WG_ROWS * 128; // one 64-row x 64-element bf16 box = 8 KB
+constexpr int WG_STAGES_MAX = 4;
+
+struct WgradPlan {
+    int NT;          // 128-row output tiles along n
+    int KW;          // k-slice width per CTA (multiple of 16, <= 256)
+    int k_groups;    // slices along k
+    int per_group;   // n-tiles per CTA (per_group * KW <= 512)
+    int n_groups;
+    int kw_boxes;    // ceil(KW / 64)
+    int chunks;      // row chunks per batch entry
+    long long chunk_rows;   // multiple of WG_ROWS
+    int stages;
+    int stage_bytes;
+};
+
+static WgradPlan make_plan(int Bt, long long R, int K, int N) {
+    WgradPlan p;
+    p.NT = ceil_div(N, 128);
+    int kg = ceil_div(K, 256);
+    p.KW = (ceil_div(K, kg) + 15) / 16 * 16;
+    p.k_groups = ceil_div(K, p.KW);
+    p.kw_boxes = ceil_div(p.KW, 64);
+    p.per_group = std::max(1, std::min(p.NT, 512 / p.KW));
+    p.per_group = std::max(1, std::min(p.per_group, (13 - p.kw_boxes) / 2));   // two stages must fit in 216 KB
+    p.n_groups = ceil_div(p.NT, p.per_group);
+    p.stage_bytes = (p.per_group * 2 + p.kw_boxes) * WG_BOX_BYTES;
+    p.stages = std::max(2, std::min(WG_STAGES_MAX, (216 * 1024) / p.stage_bytes));
+    long long groups = (long long)p.k_groups * p.n_groups;
+    long long want = std::max<long long>(1, (148LL * 2 + Bt * groups - 1) / (Bt * groups));
+    long long max_chunks = std::max<long long>(1, R / 512);
+    p.chunks = (int)std::min(want, max_chunks);
+    p.chunk_rows = ((R + p.chunks - 1) / p.chunks + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+    p.chunks = (int)((R + p.chunk_rows - 1) / p.chunk_rows);
+    return p;
+}
+
+struct WgradParams {
+    int Bt, K, N;
+    long long R;
+    WgradPlan plan;
+    float* partial;     // [Bt][chunks][N][K]
+};
+
+__global__ void __launch_bounds__(256, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmA, WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[WG_STAGES_MAX], empty_bar[WG_STAGES_MAX], done_bar;
+    __shared__ uint32_t tmem_base_s;
+    const WgradPlan& pl = p.plan;
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // blockIdx.x = group (k-slice fastest), blockIdx.y = chunk, blockIdx.z = batch entry
+    const int kg = blockIdx.x % pl.k_groups, ng = blockIdx.x / pl.k_groups;
+    const int chunk = blockIdx.y, b = blockIdx.z;
+    const int nt0 = ng * pl.per_group;
+    const int ntiles = min(pl.per_group, pl.NT - nt0);
+    const int k0 = kg * pl.KW;
+    const long long r_begin = (long long)chunk * pl.chunk_rows;
+    const long long r_end = min(p.R, r_begin + pl.chunk_rows);
+    const int iters = (int)((r_end - r_begin + WG_ROWS - 1) / WG_ROWS);
+    const int d_bytes = pl.per_group * 2 * WG_BOX_BYTES;   // dC part of a stage
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmD);
+        tma_prefetch_desc(&tmA);
+        for (int s = 0; s < pl.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            const uint32_t tx = (uint32_t)((ntiles * 2 + pl.kw_boxes) * WG_BOX_BYTES);
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], tx);
+                uint8_t* st = tiles + (size_t)s * pl.stage_bytes;
+                const int r = (int)(r_begin + (long long)it * WG_ROWS);
+                for (int j = 0; j < ntiles * 2; ++j)
+                    tma_load_3d(st + j * WG_BOX_BYTES, &tmD, &full_bar[s], (nt0 * 2 + j) * 64, r, b);
+                for (int j = 0; j < pl.kw_boxes; ++j)
+                    tma_load_3d(st + d_bytes + j * WG_BOX_BYTES, &tmA, &full_bar[s], k0 + j * 64, r, b);
+                if (++s == pl.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, pl.KW, 1, 1);
+            int s = 0; uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(tiles + (size_t)s * pl.stage_bytes);
+                for (int j = 0; j < ntiles; ++j) {
+#pragma unroll
+                    for (int ks = 0; ks < WG_ROWS / 16; ++ks) {     // 16 rows = 2 swizzle atoms = 2 KB
+                        const uint64_t adesc = make_desc(sb + j * 2 * WG_BOX_BYTES + ks * 2048, WG_BOX_BYTES, 1024);
+                        const uint64_t bdesc = make_desc(sb + d_bytes + ks * 2048, WG_BOX_BYTES, 1024);
+                        umma_bf16(tmem_base + (uint32_t)(j * pl.KW), adesc, bdesc, idesc, (it | ks) != 0);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+                if (++s == pl.stages) { s = 0; ph ^= 1; }
+            }
+            umma_commit(&done_bar);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        mbar_wait(&done_bar, 0);
+        tc_fence_after();
+        float* out = p.partial + ((long long)b * pl.chunks + chunk) * p.N * p.K;
+        for (int j = 0; j < ntiles; ++j) {
+            const int n = (nt0 + j) * 128 + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * pl.KW);
+            for (int c0 = 0; c0 < pl.KW; c0 += 16) {
+                uint32_t r[16];
+                if (iters > 0) {
+                    tmem_ld16(taddr + (uint32_t)c0, r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = 0u;
+                }
+                const int k = k0 + c0;
+                if (n < p.N && k < p.K) {
+                    float* dst = out + (long long)n * p.K + k;
+                    const int nv = min(16, p.K - k);            // 8 or 16
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(r[0], r[1], r[2], r[3]);
+                    *reinterpret_cast<uint4*>(dst + 4) = make_uint4(r[4], r[5], r[6], r[7]);
+                    if (nv > 8) {
+                        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(r[8], r[9], r[10], r[11]);
+                        *reinterpret_cast<uint4*>(dst + 12) = make_uint4(r[12], r[13], r[14], r[15]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// dW[n][k] = sum_b gate[b][k] * sum_c partial[b][c][n][k]; leaves P_b in partial[b][0] when chunks > 1
+__global__ void wgrad_reduce_kernel(float* __restrict__ partial, const float* __restrict__ gate,
+                                    float* __restrict__ dW, int Bt, int chunks, int N, int K) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long NK = (long long)N * K;
+    if (idx >= NK) return;
+    const int k = (int)(idx % K);
+    float acc = 0.f;
+    for (int b = 0; b < Bt; ++b) {
+        float* pb = partial + (long long)b * chunks * NK + idx;
+        float s = pb[0];
+        for (int c = 1; c < chunks; ++c) s += pb[(long long)c * NK];
+        if (chunks > 1 && gate) pb[0] = s;
+        acc = gate ? fmaf(gate[(long long)b * K + k], s, acc) : acc + s;
+    }
+    dW[idx] = acc;
+}
+
+// dgate[b][k] = sum_n W[n][k] * P_b[n][k]
+__global__ void wgrad_dgate_kernel(const float* __restrict__ partial, const float* __restrict__ W,
+                                   float* __restrict__ dgate, int Bt, int chunks, int N, int K) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (k >= K) return;
+    const float* pb = partial + (long long)b * chunks * N * K;
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc = fmaf(W[(long long)n * K + k], pb[(long long)n * K + k], acc);
+    dgate[(long long)b * K + k] = acc;
+}
+
+}  // namespace tc
+}  // namespace pb
+
+using namespace pb;
+using namespace pb::tc;
+
+extern "C" long long pb_pw_wgrad_tc_workspace_bytes(int Bt, long long R, int K, int N) {
+    if (Bt <= 0 || R <= 0 || K <= 0 || N <= 0) return 0;
+    WgradPlan pl = make_plan(Bt, R, K, N);
+    return (long long)Bt * pl.chunks * N * K * (long long)sizeof(float);
+}
+
+extern "C" int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, const float* Wf32, void* workspace,
+                              float* dW, float* dgate, int Bt, long long R, int K, int N, pb_stream_t stream) {
+    PB_REQUIRE(A && dC && workspace && dW, "pw_wgrad_tc: null pointer");
+    PB_REQUIRE(Bt > 0 && Bt <= 65535 && R > 0 && K > 0 && N > 0, "pw_wgrad_tc: bad problem size");
+    PB_REQUIRE(K % 8 == 0 && N % 8 == 0, "pw_wgrad_tc: K=%d and N=%d must be multiples of 8", K, N);
+    PB_REQUIRE(!dgate || (Wf32 != nullptr), "pw_wgrad_tc: dgate needs the fp32 weights");
+    WgradParams p;
+    p.Bt = Bt; p.K = K; p.N = N; p.R = R;
+    p.plan = make_plan(Bt, R, K, N);
+    p.partial = (float*)workspace;
+    const WgradPlan& pl = p.plan;
+    PB_REQUIRE(pl.chunks <= 65535, "pw_wgrad_tc: too many row chunks");
+    CUtensorMap tmD, tmA;
+    {
+        uint64_t dims[3] = {(uint64_t)N, (uint64_t)R, (uint64_t)Bt};
+        uint64_t str[3] = {2, (uint64_t)N * 2, (uint64_t)R * N * 2};
+        uint32_t box[3] = {64, WG_ROWS, 1};
+        if (int e = make_tmap_bf16(&tmD, dC, 3, dims, str, box)) return e;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)K, (uint64_t)R, (uint64_t)Bt};
+        uint64_t str[3] = {2, (uint64_t)K * 2, (uint64_t)R * K * 2};
+        uint32_t box[3] = {64, WG_ROWS, 1};
+        if (int e = make_tmap_bf16(&tmA, A, 3, dims, str, box)) return e;
+    }
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    });
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_tc_kernel)");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(pl.k_groups * pl.n_groups, pl.chunks, Bt);
+    const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024;
+    wgrad_tc_kernel<<<grid, 256, smem, st>>>(tmD, tmA, p);
+    PB_CHECK_LAUNCH("wgrad_tc_kernel");
+    const long long NK = (long long)N * K;
+    wgrad_reduce_kernel<<<ceil_div(NK, 256), 256, 0, st>>>(p.partial, gate, dW, Bt, pl.chunks, N, K);
+    PB_CHECK_LAUNCH("wgrad_reduce_kernel");
+    if (dgate) {
+        dim3 g2(ceil_div(K, 128), Bt);
+        wgrad_dgate_kernel<<<g2, 128, 0, st>>>(p.partial, Wf32, dgate, Bt, pl.chunks, N, K);
+        PB_CHECK_LAUNCH("wgrad_dgate_kernel");
+    }
+    return PB_OK;
+}

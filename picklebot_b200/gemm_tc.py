@@ -1,11 +1,12 @@
-"""Launchers for the tcgen05 / TMEM / TMA GEMM kernels (csrc/pwgemm_tc.cu)."""
+"""Launchers for the tcgen05 / TMEM / TMA GEMM kernels (csrc/pwgemm_tc.cu, csrc/pwwgrad_tc.cu)."""
 from __future__ import annotations
 
 import os
+from typing import Optional, Tuple
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .ops import _chk, _p, _st, call
 
 # The tensor-core path is the production path for bf16; PB_GEMM=simt (see ops.py) turns it off.
@@ -15,7 +16,8 @@ _WGRAD_READY = os.environ.get("PB_TC_WGRAD", "1") != "0"
 
 def gemm(A: torch.Tensor, Wb: torch.Tensor, N: int, K: int, Bw: int = 1, Bt: int = 1, bias=None, colscale=None,
          coladd=None) -> torch.Tensor:
-    """A bf16 [Bt][R][K] (contiguous), Wb bf16 [Bw][N][K] -> bf16 [Bt*R][N]."""
+    """A bf16 [Bt][R][K] (contiguous), Wb bf16 [Bw][N][K] -> bf16 [Bt*R][N];
+    C = (A W^T + bias) * colscale[b] + coladd[b]."""
     _chk(A, "gemm_tc.A"); _chk(Wb, "gemm_tc.W")
     assert A.dtype == torch.bfloat16 and Wb.dtype == torch.bfloat16
     rows = A.numel() // K
@@ -27,4 +29,22 @@ def gemm(A: torch.Tensor, Wb: torch.Tensor, N: int, K: int, Bw: int = 1, Bt: int
 
 
 def wgrad_ready() -> bool:
-    return False
+    return _WGRAD_READY and ops._TC_READY
+
+
+def wgrad(A: torch.Tensor, dC: torch.Tensor, K: int, N: int, gate: Optional[torch.Tensor] = None,
+          W: Optional[torch.Tensor] = None, Bt: int = 1, want_dgate: bool = False
+          ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """dW[n][k] = sum_b gate[b][k] * sum_r dC[b][r][n] A[b][r][k]  (fp32 [N][K]);
+    optionally dgate[b][k] = sum_n W[n][k] * (sum_r dC A)[b]."""
+    _chk(A, "wgrad_tc.A"); _chk(dC, "wgrad_tc.dC")
+    assert A.dtype == torch.bfloat16 and dC.dtype == torch.bfloat16
+    rows = A.numel() // K
+    R = rows // Bt
+    nbytes_ws = int(_lib.lib().pb_pw_wgrad_tc_workspace_bytes(Bt, R, K, N))
+    ws = torch.empty((nbytes_ws // 4,), dtype=torch.float32, device=A.device)
+    dW = torch.empty((N, K), dtype=torch.float32, device=A.device)
+    dgate = torch.empty((Bt, K), dtype=torch.float32, device=A.device) if want_dgate else None
+    call("pb_pw_wgrad_tc", A.data_ptr(), dC.data_ptr(), _p(gate), _p(W), ws.data_ptr(), dW.data_ptr(), _p(dgate),
+         Bt, R, K, N, _st(), nbytes=(A.numel() + dC.numel()) * 2 + N * K * 4)
+    return dW, dgate

@@ -57,3 +57,27 @@ def test_gemm_tc_matches_simt_bitwise_scale():
     a = gemm_tc.gemm(A, W.bfloat16(), N, K)
     b = ops.gemm_simt(A, W, N, K, K, 1)
     assert rel_err(a.float(), b.float()) < 3e-3
+
+
+# (Bt, R, K, N): K = input channels of the layer, N = its output channels
+WGRAD_CASES = [(1, 4096, 16, 16), (1, 100000, 16, 64), (1, 7000, 24, 72), (1, 50000, 72, 24), (2, 931, 960, 160),
+               (1, 59584, 160, 960), (3, 777, 672, 112), (1, 3000, 112, 672), (4, 100, 72, 40), (1, 12544, 80, 184),
+               (64, 735, 960, 160), (1, 65, 8, 8), (2, 5000, 144, 576), (1, 20000, 576, 144), (1, 6000, 40, 240)]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad_tc(case):
+    from picklebot_b200 import gemm_tc
+    Bt, R, K, N = case
+    A = rnd(Bt * R, K, seed=1).bfloat16()
+    dC = rnd(Bt * R, N, seed=2).bfloat16()
+    dW, _ = gemm_tc.wgrad(A, dC, K, N)
+    ref = dC.float().t() @ A.float()
+    assert rel_err(dW, ref) < 1e-4
+    # squeeze-excite form: per-sample gate and the gate gradient from the same per-sample products
+    gate = rnd(Bt, K, seed=3).abs() + 0.1
+    W = rnd(N, K, seed=4, scale=0.3)
+    dW2, dgate = gemm_tc.wgrad(A, dC, K, N, gate=gate, W=W, Bt=Bt, want_dgate=True)
+    P = torch.einsum("brn,brk->bnk", dC.float().view(Bt, R, N), A.float().view(Bt, R, K))
+    assert rel_err(dW2, (P * gate[:, None, :]).sum(0)) < 1e-4
+    assert rel_err(dgate, (P * W[None]).sum(1)) < 1e-4
