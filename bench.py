@@ -308,6 +308,13 @@ def main():
             step_resident()
         _lib.PROFILER = None
         summ = prof.summary()
+        if os.environ.get("PB_BENCH_DETAIL"):
+            det = prof.summary(by_tag=True)
+            rows = sorted(det.items(), key=lambda kv: -kv[1]["ms"])
+            with open(os.environ["PB_BENCH_DETAIL"], "w") as f:
+                for k, v in rows:
+                    gb = v["bytes"] / (v["ms"] * 1e6) if v["ms"] > 0 else 0
+                    f.write(f"{v['ms']:9.3f} ms  {v['launches']:4d}x  {gb:8.1f} GB/s  {k}\n")
         tot_ms = sum(v["ms"] for v in summ.values())
         for name, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"]):
             gbs = v["bytes"] / (v["ms"] * 1e6) if v["ms"] > 0 else 0.0

@@ -90,14 +90,14 @@ class KernelProfiler:
     live roofline numbers; off (None) by default so the hot path pays nothing."""
 
     def __init__(self):
-        self.records = []          # (name, start_event, end_event, algorithmic_bytes)
+        self.records = []          # (name, start_event, end_event, algorithmic_bytes, tag)
 
-    def summary(self):
+    def summary(self, by_tag: bool = False):
         import torch
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, nbytes in self.records:
-            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+        for name, e0, e1, nbytes, tag in self.records:
+            d = out.setdefault(name if not by_tag else f"{name}|{tag}", {"launches": 0, "ms": 0.0, "bytes": 0})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
             d["bytes"] += nbytes
@@ -107,7 +107,7 @@ class KernelProfiler:
 PROFILER = None
 
 
-def call(name: str, *args, nbytes: int = 0) -> None:
+def call(name: str, *args, nbytes: int = 0, tag: str = "") -> None:
     prof = PROFILER
     if prof is not None:
         import torch
@@ -120,7 +120,7 @@ def call(name: str, *args, nbytes: int = 0) -> None:
         raise PicklebotKernelError(f"{name} failed (code {rc}): {msg.decode() if msg else '?'}")
     if prof is not None:
         e1.record()
-        prof.records.append((name, e0, e1, nbytes))
+        prof.records.append((name, e0, e1, nbytes, tag))
 
 
 def launch_count() -> int:

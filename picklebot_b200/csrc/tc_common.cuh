@@ -22,14 +22,15 @@ EncodeTiledFn encode_fn();   // defined in pwgemm_tc.cu; nullptr if the driver l
 // bf16 tensor, up to 3 dims (innermost first), 128-byte swizzle, zero fill out of bounds.
 // dims[i] / strides_bytes[i] (stride of dim i, i >= 1) / box[i].
 static inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
-                                 const uint64_t* strides_bytes, const uint32_t* box) {
+                                 const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128 = true) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled unavailable in this driver"); return PB_ERR_UNSUPPORTED; }
-    cuuint64_t gdim[5]; cuuint64_t gstr[5]; cuuint32_t bx[5]; cuuint32_t es[5];
+    cuuint64_t gdim[5]; cuuint64_t gstr[5] = {0, 0, 0, 0, 0}; cuuint32_t bx[5]; cuuint32_t es[5];
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i + 1];
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu] box [%u,%u,%u]", (int)r, rank,
@@ -82,6 +83,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "r"(c4)
         : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {

@@ -16,8 +16,10 @@ from ._lib import (ACT_HSIGMOID, ACT_HSWISH, ACT_LRELU, ACT_NONE, ACT_RELU, PB_B
                    PB_U8)
 
 
-def call(name, *args, nbytes=0):
-    _lib.call(name, *args, nbytes=nbytes)
+def call(name, *args, nbytes=0, tag=""):
+    if _lib.PROFILER is not None and not tag:
+        tag = ",".join(str(a) for a in args if isinstance(a, int) and not isinstance(a, bool) and 0 < a < 100000)
+    _lib.call(name, *args, nbytes=nbytes, tag=tag)
 
 ACT_CODES = {"none": ACT_NONE, "relu": ACT_RELU, "hswish": ACT_HSWISH, "lrelu": ACT_LRELU,
              "hsigmoid": ACT_HSIGMOID}

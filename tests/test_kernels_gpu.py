@@ -38,6 +38,17 @@ DW_CASES = [
     (1, 240, 7, 6, 6, (5, 3, 3), (1, 2, 2), (2, 1, 1)),       # movinet 5x3x3
     (1, 960, 3, 7, 7, (1, 5, 5), (1, 1, 1), (2, 2, 2)),       # widest layer
     (2, 8, 1, 1, 1, (1, 3, 3), (1, 1, 1), (1, 1, 1)),         # degenerate 1x1x1 frame
+    # MobileNetLarge3D's own layer shapes, 2 clips
+    (2, 16, 8, 112, 112, (1, 3, 3), (1, 1, 1), (1, 1, 1)),    # block2.0
+    (2, 64, 10, 112, 112, (1, 3, 3), (2, 2, 2), (1, 1, 1)),   # block2.1
+    (2, 72, 6, 56, 56, (1, 3, 3), (1, 1, 1), (1, 1, 1)),      # block2.2
+    (2, 72, 8, 56, 56, (1, 5, 5), (2, 2, 2), (2, 2, 2)),      # block3.0
+    (2, 120, 6, 28, 28, (1, 5, 5), (1, 1, 1), (2, 2, 2)),     # block3.1
+    (2, 240, 14, 28, 28, (1, 3, 3), (2, 2, 2), (1, 1, 1)),    # block4.0
+    (2, 184, 10, 14, 14, (1, 3, 3), (1, 1, 1), (1, 1, 1)),    # block4.2
+    (2, 672, 16, 14, 14, (1, 3, 3), (1, 1, 1), (1, 1, 1)),    # block4.5
+    (2, 672, 18, 14, 14, (1, 5, 5), (2, 2, 2), (2, 2, 2)),    # block5.0
+    (2, 960, 11, 7, 7, (1, 5, 5), (1, 1, 1), (2, 2, 2)),      # block5.1
 ]
 
 
