@@ -1,18 +1,19 @@
 // Depthwise (1,k,k) convolution fast paths for bf16 NDHWC activations: TMA-staged halo tiles.
 //
 // A persistent CTA owns one channel block (<= 128 channels) and walks over (sample, frame, h-tile, w-tile)
-// work items.  For each item cp.async.bulk.tensor.5d fetches the halo tile [Hi][Wi][Cb] of the input frame
-// (and, for the weight gradient, the matching dy tile) into a shared-memory ring; out-of-bounds
-// coordinates are zero-filled by the TMA unit, so spatial padding costs nothing and needs no bounds
-// checks, and the frames created by the reference's scalar temporal padding (mobilenet.py:67-75) are
-// written as zeros without reading anything.  Each thread owns 4 channels (8-byte vectors) and a strip of
-// output pixels: every staged vector is unpacked once and fed to all the outputs of the strip that use it
-// with packed fp32 FMAs (fma.rn.f32x2); filter taps stay in registers.
+// work items.  A dedicated producer warp issues one cp.async.bulk.tensor.5d per item: the halo tile
+// [Hi][Wi][Cb] of the source frame (plus, for the weight gradient, the matching dy tile) lands in a
+// shared-memory ring guarded by full/empty mbarriers, so the eight consumer warps never wait for each
+// other -- only for data.  Out-of-bounds coordinates are zero-filled by the TMA unit: spatial padding costs
+// nothing and needs no bounds checks, and the frames created by the reference's scalar temporal padding
+// (mobilenet.py:67-75) are written as zeros without reading anything.  Each consumer thread owns 4 channels
+// (8-byte vectors) and a strip of output pixels: every staged vector is unpacked once and fed to all the
+// outputs of the strip that use it with packed fp32 FMAs (fma.rn.f32x2); filter taps stay in registers.
 //
 //   forward            : y  = conv(x, w)                     (also the stride-1 input gradient: flipped w)
 //   input gradient, s=2: dx = gather of dy over the taps whose parity matches
 //   weight gradient    : dw accumulated in registers over all tiles of the CTA, reduced once at the end
-//                        (warp shuffles, shared memory, then one fp32 atomic per tap and channel per CTA)
+//                        (shared-memory sums, then one fp32 atomic per tap and channel per CTA)
 #include <algorithm>
 #include <mutex>
 
@@ -24,12 +25,12 @@ namespace pb {
 using namespace tc;
 
 constexpr int DWT_MAX_STAGES = 4;
-constexpr int DWT_THREADS = 256;
+constexpr int DWT_CONSUMERS = 224;                 // 7 consumer warps (2 CTAs x 256 threads x 128 regs per SM)
+constexpr int DWT_THREADS = DWT_CONSUMERS + 32;    // + 1 producer warp
 constexpr int DWT_MAX_ZF = 64;
 
 struct DwTile {
     int B, C;
-    int Ti, Hin, Win;          // tensor that is staged through TMA ("source")
     int To, Ho, Wo;            // tensor the tiles are defined on ("destination")
     int pS;                    // spatial padding of the convolution
     int Cb, Gb, nblk;          // channel block, 4-channel groups per block, number of blocks
@@ -51,34 +52,80 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
     d = *reinterpret_cast<float2*>(&dd);
 }
 __device__ __forceinline__ float2 unpack2(uint32_t u) { return make_float2(bf16_lo(u), bf16_hi(u)); }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
 
-struct TileCoord { int b, n, h0, w0; };
+// shared bookkeeping of the tile pipeline
+struct TileCtx {
+    uint64_t full[DWT_MAX_STAGES];
+    uint64_t empty[DWT_MAX_STAGES];
+    int4 coord[DWT_MAX_STAGES];            // (b, n-th valid frame, h0, w0) of the tile in each stage
+};
 
-__device__ __forceinline__ TileCoord decode_tile(const DwTile& p, long long t) {
-    TileCoord c;
+__device__ __forceinline__ int4 decode_tile(const DwTile& p, long long t) {
+    int4 c;
     int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
     int th = (int)(t % p.tiles_h); t /= p.tiles_h;
-    c.n = (int)(t % p.f_count);
-    c.b = (int)(t / p.f_count);
-    c.h0 = th * p.Ht; c.w0 = tw * p.Wt;
+    c.y = (int)(t % p.f_count);
+    c.x = (int)(t / p.f_count);
+    c.z = th * p.Ht; c.w = tw * p.Wt;
     return c;
 }
 
-// zero the destination frames that have no source frame (only CTAs with blockIdx.y == 0 call this)
-__device__ __forceinline__ void zero_frames(const DwTile& p, __nv_bfloat16* y) {
+// zero the destination frames that have no source frame (consumer threads of CTAs with blockIdx.y == 0)
+__device__ __forceinline__ void zero_frames(const DwTile& p, __nv_bfloat16* y, int tid) {
     if (p.nzf <= 0) return;
-    const long long frame16 = (long long)p.Ho * p.Wo * p.C / 8;
-    const long long total = (long long)p.B * p.nzf * frame16;
+    // every CTA of the grid (all channel blocks) takes whole frames round-robin; a frame is contiguous
+    const int frame16 = (int)((long long)p.Ho * p.Wo * p.C / 8);
+    const int nframes = p.B * p.nzf;
+    const int ncta = gridDim.x * gridDim.y;
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (long long i = (long long)blockIdx.x * DWT_THREADS + threadIdx.x; i < total;
-         i += (long long)gridDim.x * DWT_THREADS) {
-        long long e = i % frame16;
-        long long q = i / frame16;
-        int f = p.zf[(int)(q % p.nzf)];
-        int b = (int)(q / p.nzf);
-        reinterpret_cast<uint4*>(y)[((long long)b * p.To + f) * frame16 + e] = z;
+    for (int q = blockIdx.y * gridDim.x + blockIdx.x; q < nframes; q += ncta) {
+        const int f = p.zf[q % p.nzf];
+        const int b = q / p.nzf;
+        uint4* dst = reinterpret_cast<uint4*>(y) + ((long long)b * p.To + f) * frame16;
+        for (int e = tid; e < frame16; e += DWT_CONSUMERS) dst[e] = z;
     }
 }
+
+__device__ __forceinline__ void pipeline_init(TileCtx& cx, const DwTile& p) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&cx.full[s], 1); mbar_init(&cx.empty[s], DWT_CONSUMERS / 32); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+}
+
+// Producer warp (one elected lane): `load(stage_ptr, full_barrier, coord)` issues the TMA copies of one tile.
+template <typename LoadFn>
+__device__ __forceinline__ void producer_loop(TileCtx& cx, const DwTile& p, uint8_t* ring, long long my_tiles,
+                                              uint32_t tx_bytes, LoadFn load) {
+    for (long long n = 0; n < my_tiles; ++n) {
+        const int s = (int)(n % p.stages);
+        if (n >= p.stages) mbar_wait(&cx.empty[s], (uint32_t)(((n / p.stages) - 1) & 1));
+        const int4 c = decode_tile(p, blockIdx.x + n * (long long)gridDim.x);
+        cx.coord[s] = c;
+        mbar_expect_tx(&cx.full[s], tx_bytes);          // release: publishes coord[s] as well
+        load(ring + (size_t)s * p.stage_bytes, &cx.full[s], c);
+    }
+}
+
+// per-thread work split: thread = (slot, group); items of a tile are (row, strip) pairs, item = slot + n*ppp
+struct ItemIter {
+    int hl, strip, d_h, d_s, nstrips;
+    __device__ __forceinline__ void start(int slot, int ppp, int nstrips_) {
+        nstrips = nstrips_;
+        hl = slot / nstrips; strip = slot % nstrips;
+        d_h = ppp / nstrips; d_s = ppp % nstrips;
+    }
+    __device__ __forceinline__ void next() {
+        hl += d_h; strip += d_s;
+        if (strip >= nstrips) { strip -= nstrips; ++hl; }
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // forward (and stride-1 dgrad): destination tile [Ht][Wt], source halo [(Ht-1)S+K][(Wt-1)S+K]
@@ -88,22 +135,27 @@ __global__ void __launch_bounds__(DWT_THREADS, 2)
 dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w_tc,
                   __nv_bfloat16* __restrict__ y, const DwTile p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[DWT_MAX_STAGES];
+    __shared__ TileCtx cx;
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* ring = smem_raw + (((raw + 127u) & ~127u) - raw);
     const int tid = threadIdx.x;
     const int c_base = blockIdx.y * p.Cb;
     const int cb_bytes = p.Cb * 2;
+    pipeline_init(cx, p);
+    const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (tid == 0) {
-        tma_prefetch_desc(&tmX);
-        for (int s = 0; s < p.stages; ++s) mbar_init(&full_bar[s], 1);
-        fence_barrier_init();
+    if (tid >= DWT_CONSUMERS) {
+        if (tid == DWT_CONSUMERS) {
+            tma_prefetch_desc(&tmX);
+            producer_loop(cx, p, ring, my_tiles, (uint32_t)p.box_bytes, [&](uint8_t* st, uint64_t* bar, const int4& c) {
+                tma_load_5d(st, &tmX, bar, c_base, c.w * S - p.pS, c.z * S - p.pS, p.src_first + c.y * p.src_step, c.x);
+            });
+        }
+        return;
     }
-    __syncthreads();
-    if (blockIdx.y == 0) zero_frames(p, y);
+    zero_frames(p, y, tid);
 
-    const int ppp = DWT_THREADS / p.Gb;
+    const int ppp = DWT_CONSUMERS / p.Gb;
     const int g = tid % p.Gb;
     const bool active = tid < ppp * p.Gb && (c_base + g * 4) < p.C;
     const int slot = tid / p.Gb;
@@ -126,42 +178,35 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
             else wv[t][c] = make_float2(lo, hi);
         }
     }
-
-    const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int nstrips = p.Wt / WS;
     const int items = p.Ht * nstrips;
-
-    auto issue = [&](long long n) {
-        TileCoord tc_ = decode_tile(p, blockIdx.x + n * (long long)gridDim.x);
-        const int s = (int)(n % p.stages);
-        mbar_expect_tx(&full_bar[s], (uint32_t)p.box_bytes);
-        tma_load_5d(ring + (size_t)s * p.stage_bytes, &tmX, &full_bar[s], c_base, tc_.w0 * S - p.pS, tc_.h0 * S - p.pS,
-                    p.src_first + tc_.n * p.src_step, tc_.b);
-    };
-    if (tid == 0)
-        for (long long n = 0; n < my_tiles && n < p.stages; ++n) issue(n);
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t row_bytes = (uint32_t)(p.Wi * cb_bytes);
+    const int lane = tid & 31;
 
     for (long long n = 0; n < my_tiles; ++n) {
         const int s = (int)(n % p.stages);
-        mbar_wait(&full_bar[s], (uint32_t)((n / p.stages) & 1));
-        const TileCoord tc_ = decode_tile(p, blockIdx.x + n * (long long)gridDim.x);
-        const int to = p.f_first + tc_.n * p.f_step;
-        const uint8_t* tile = ring + (size_t)s * p.stage_bytes;
+        mbar_wait(&cx.full[s], (uint32_t)((n / p.stages) & 1));
+        const int4 c = cx.coord[s];
+        const int to = p.f_first + c.y * p.f_step;
+        const uint32_t tile = ring_u32 + (uint32_t)(s * p.stage_bytes) + (uint32_t)(g * 8);
         if (active) {
-            for (int it = slot; it < items; it += ppp) {
-                const int strip = it % nstrips, hl = it / nstrips;
-                const int ho = tc_.h0 + hl;
-                if (ho >= p.Ho) continue;
+            ItemIter it;
+            it.start(slot, ppp, nstrips);
+            for (int idx = slot; idx < items; idx += ppp, it.next()) {
+                const int ho = c.z + it.hl;
+                if (ho >= p.Ho) break;
                 float2 acc[WS][2];
 #pragma unroll
                 for (int o = 0; o < WS; ++o) { acc[o][0] = make_float2(0.f, 0.f); acc[o][1] = make_float2(0.f, 0.f); }
+                uint32_t rowa = tile + (uint32_t)(it.hl * S) * row_bytes + (uint32_t)(it.strip * WS * S * cb_bytes);
 #pragma unroll
-                for (int i = 0; i < K; ++i) {
-                    const uint8_t* rowp = tile + ((size_t)(hl * S + i) * p.Wi + (size_t)strip * WS * S) * cb_bytes + g * 8;
+                for (int i = 0; i < K; ++i, rowa += row_bytes) {
+                    uint32_t a = rowa;
                     if constexpr (!PACKED) {
 #pragma unroll
-                        for (int j = 0; j < (WS - 1) * S + K; ++j) {
-                            const uint2 u = *reinterpret_cast<const uint2*>(rowp + (size_t)j * cb_bytes);
+                        for (int j = 0; j < (WS - 1) * S + K; ++j, a += cb_bytes) {
+                            const uint2 u = lds64(a);
                             const float2 v0 = unpack2(u.x), v1 = unpack2(u.y);
 #pragma unroll
                             for (int o = 0; o < WS; ++o) {
@@ -176,8 +221,8 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
                         constexpr int NJ = (WS - 1) * S + K;
                         float2 win[NJ][2];
 #pragma unroll
-                        for (int j = 0; j < NJ; ++j) {
-                            const uint2 u = *reinterpret_cast<const uint2*>(rowp + (size_t)j * cb_bytes);
+                        for (int j = 0; j < NJ; ++j, a += cb_bytes) {
+                            const uint2 u = lds64(a);
                             win[j][0] = unpack2(u.x); win[j][1] = unpack2(u.y);
                         }
 #pragma unroll
@@ -191,27 +236,28 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
                         }
                     }
                 }
-                const int wo0 = tc_.w0 + strip * WS;
-                __nv_bfloat16* yp = y + ((((long long)tc_.b * p.To + to) * p.Ho + ho) * p.Wo + wo0) * p.C + c_base + g * 4;
+                const int wo0 = c.w + it.strip * WS;
+                __nv_bfloat16* yp = y + ((((long long)c.x * p.To + to) * p.Ho + ho) * p.Wo + wo0) * p.C + c_base + g * 4;
 #pragma unroll
                 for (int o = 0; o < WS; ++o) {
                     if (wo0 + o < p.Wo) {
                         uint2 out;
                         out.x = pack_bf16x2(acc[o][0].x, acc[o][0].y);
                         out.y = pack_bf16x2(acc[o][1].x, acc[o][1].y);
-                        *reinterpret_cast<uint2*>(yp + (long long)o * p.C) = out;
+                        *reinterpret_cast<uint2*>(yp) = out;
                     }
+                    yp += p.C;
                 }
             }
         }
-        __syncthreads();                                  // everyone is done reading stage s
-        if (tid == 0 && n + p.stages < my_tiles) issue(n + p.stages);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cx.empty[s]);          // this warp is done reading stage s
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // stride-2 input gradient: destination tile of dx [Ht][Wt] (Ht, Wt even, tile origin even), source halo of
-// dy rows ho_base .. ho_base + Ht/2 + (K-1)/2, same for columns.
+// dy rows h0/2 - P/2 .. , same for columns.
 //   dx[h][w] = sum_{i,j : (h+p-i), (w+p-j) even} dy[(h+p-i)/2][(w+p-j)/2] * w[i][j]
 // ------------------------------------------------------------------------------------------------
 template <int K, int XS>
@@ -219,24 +265,28 @@ __global__ void __launch_bounds__(DWT_THREADS, 2)
 dw_dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmD, const float* __restrict__ w_tc,
                        __nv_bfloat16* __restrict__ dx, const DwTile p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[DWT_MAX_STAGES];
+    __shared__ TileCtx cx;
     constexpr int P = K / 2;
-    constexpr int HALF = (K - 1) / 2;         // extra dy rows/cols on the low side: p/2 rounded down is P/2
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* ring = smem_raw + (((raw + 127u) & ~127u) - raw);
     const int tid = threadIdx.x;
     const int c_base = blockIdx.y * p.Cb;
     const int cb_bytes = p.Cb * 2;
+    pipeline_init(cx, p);
+    const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (tid == 0) {
-        tma_prefetch_desc(&tmD);
-        for (int s = 0; s < p.stages; ++s) mbar_init(&full_bar[s], 1);
-        fence_barrier_init();
+    if (tid >= DWT_CONSUMERS) {
+        if (tid == DWT_CONSUMERS) {
+            tma_prefetch_desc(&tmD);
+            producer_loop(cx, p, ring, my_tiles, (uint32_t)p.box_bytes, [&](uint8_t* st, uint64_t* bar, const int4& c) {
+                tma_load_5d(st, &tmD, bar, c_base, c.w / 2 - P / 2, c.z / 2 - P / 2, p.src_first + c.y * p.src_step, c.x);
+            });
+        }
+        return;
     }
-    __syncthreads();
-    if (blockIdx.y == 0) zero_frames(p, dx);
+    zero_frames(p, dx, tid);
 
-    const int ppp = DWT_THREADS / p.Gb;
+    const int ppp = DWT_CONSUMERS / p.Gb;
     const int g = tid % p.Gb;
     const bool active = tid < ppp * p.Gb && (c_base + g * 4) < p.C;
     const int slot = tid / p.Gb;
@@ -252,56 +302,49 @@ dw_dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmD, const float* __r
             }
             wp[t][c] = pack_bf16x2(lo, hi);
         }
-
-    const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int nstrips = p.Wt / XS;
     const int items = p.Ht * nstrips;
-    (void)HALF;
-
-    auto issue = [&](long long n) {
-        TileCoord tc_ = decode_tile(p, blockIdx.x + n * (long long)gridDim.x);
-        const int s = (int)(n % p.stages);
-        mbar_expect_tx(&full_bar[s], (uint32_t)p.box_bytes);
-        tma_load_5d(ring + (size_t)s * p.stage_bytes, &tmD, &full_bar[s], c_base, tc_.w0 / 2 - P / 2, tc_.h0 / 2 - P / 2,
-                    p.src_first + tc_.n * p.src_step, tc_.b);
-    };
-    if (tid == 0)
-        for (long long n = 0; n < my_tiles && n < p.stages; ++n) issue(n);
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t row_bytes = (uint32_t)(p.Wi * cb_bytes);
+    const int lane = tid & 31;
 
     for (long long n = 0; n < my_tiles; ++n) {
         const int s = (int)(n % p.stages);
-        mbar_wait(&full_bar[s], (uint32_t)((n / p.stages) & 1));
-        const TileCoord tc_ = decode_tile(p, blockIdx.x + n * (long long)gridDim.x);
-        const int t_dst = p.f_first + tc_.n * p.f_step;
-        const uint8_t* tile = ring + (size_t)s * p.stage_bytes;
+        mbar_wait(&cx.full[s], (uint32_t)((n / p.stages) & 1));
+        const int4 c = cx.coord[s];
+        const int t_dst = p.f_first + c.y * p.f_step;
+        const uint32_t tile = ring_u32 + (uint32_t)(s * p.stage_bytes) + (uint32_t)(g * 8);
         if (active) {
-            for (int it = slot; it < items; it += ppp) {
-                const int strip = it % nstrips, hl = it / nstrips;
-                const int h = tc_.h0 + hl;
-                if (h >= p.Ho) continue;
+            ItemIter it;
+            it.start(slot, ppp, nstrips);
+            for (int idx = slot; idx < items; idx += ppp, it.next()) {
+                const int hl = it.hl;
+                const int h = c.z + hl;
+                if (h >= p.Ho) break;
                 float2 acc[XS][2];
 #pragma unroll
                 for (int o = 0; o < XS; ++o) { acc[o][0] = make_float2(0.f, 0.f); acc[o][1] = make_float2(0.f, 0.f); }
-                // local dy column of tap j for dx column xl (tile origin even): (xl + P - j)/2 + P/2
-                // the strip starts at an even xl0, so parities are compile-time per o
+                // tile origin even => parity of h equals parity of hl; the strip starts at an even column, so
+                // column parities are compile-time per o.  Local dy row/col of tap (i,j): (x + P - j)/2 + P/2.
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
-                    if (((hl + P - i) & 1) != 0) continue;                 // tile origin even: parity of h == hl
-                    const int rl = ((hl + P - i) >> 1) + P / 2;            // local dy row
-                    const uint8_t* rowp = tile + ((size_t)rl * p.Wi + (size_t)(strip * XS / 2)) * cb_bytes + g * 8;
-                    constexpr int NC = XS / 2 + (K - 1) / 2 + 1;            // dy columns a strip can touch
+                    if (((hl + P - i) & 1) != 0) continue;
+                    const int rl = ((hl + P - i) >> 1) + P / 2;
+                    uint32_t a = tile + (uint32_t)rl * row_bytes + (uint32_t)((it.strip * XS / 2) * cb_bytes);
+                    constexpr int NC = XS / 2 + P / 2 + 1;               // dy columns a strip can touch
                     float2 win[NC][2];
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        const uint2 u = *reinterpret_cast<const uint2*>(rowp + (size_t)c * cb_bytes);
-                        win[c][0] = unpack2(u.x); win[c][1] = unpack2(u.y);
+                    for (int cc = 0; cc < NC; ++cc, a += cb_bytes) {
+                        const uint2 u = lds64(a);
+                        win[cc][0] = unpack2(u.x); win[cc][1] = unpack2(u.y);
                     }
 #pragma unroll
                     for (int o = 0; o < XS; ++o) {
 #pragma unroll
                         for (int j = 0; j < K; ++j) {
                             if (((o + P - j) & 1) == 0) {
-                                const int cl = ((o + P - j) >> 1) + P / 2;   // column relative to strip*XS/2
+                                constexpr int dummy = 0; (void)dummy;
+                                const int cl = ((o + P - j) >> 1) + P / 2;
                                 const float2 w0 = unpack2(wp[i * K + j][0]), w1 = unpack2(wp[i * K + j][1]);
                                 ffma2(acc[o][0], win[cl][0], w0);
                                 ffma2(acc[o][1], win[cl][1], w1);
@@ -309,21 +352,22 @@ dw_dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmD, const float* __r
                         }
                     }
                 }
-                const int x0 = tc_.w0 + strip * XS;
-                __nv_bfloat16* xp = dx + ((((long long)tc_.b * p.To + t_dst) * p.Ho + h) * p.Wo + x0) * p.C + c_base + g * 4;
+                const int x0 = c.w + it.strip * XS;
+                __nv_bfloat16* xp = dx + ((((long long)c.x * p.To + t_dst) * p.Ho + h) * p.Wo + x0) * p.C + c_base + g * 4;
 #pragma unroll
                 for (int o = 0; o < XS; ++o) {
                     if (x0 + o < p.Wo) {
                         uint2 out;
                         out.x = pack_bf16x2(acc[o][0].x, acc[o][0].y);
                         out.y = pack_bf16x2(acc[o][1].x, acc[o][1].y);
-                        *reinterpret_cast<uint2*>(xp + (long long)o * p.C) = out;
+                        *reinterpret_cast<uint2*>(xp) = out;
                     }
+                    xp += p.C;
                 }
             }
         }
-        __syncthreads();
-        if (tid == 0 && n + p.stages < my_tiles) issue(n + p.stages);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cx.empty[s]);
     }
 }
 
@@ -336,84 +380,81 @@ __global__ void __launch_bounds__(DWT_THREADS, 2)
 dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
                     float* __restrict__ dw_tc, const DwTile p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[DWT_MAX_STAGES];
+    __shared__ TileCtx cx;
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* ring = smem_raw + (((raw + 127u) & ~127u) - raw);
     const int tid = threadIdx.x;
     const int c_base = blockIdx.y * p.Cb;
     const int cb_bytes = p.Cb * 2;
     const int x_bytes = (p.box_bytes + 127) / 128 * 128;       // dy tile follows the x tile in a stage
+    pipeline_init(cx, p);
+    const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (tid == 0) {
+    if (tid == DWT_CONSUMERS) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmD);
-        for (int s = 0; s < p.stages; ++s) mbar_init(&full_bar[s], 1);
-        fence_barrier_init();
+        producer_loop(cx, p, ring, my_tiles, (uint32_t)(p.box_bytes + p.box2_bytes),
+                      [&](uint8_t* st, uint64_t* bar, const int4& c) {
+            tma_load_5d(st, &tmX, bar, c_base, c.w * S - p.pS, c.z * S - p.pS, p.src_first + c.y * p.src_step, c.x);
+            tma_load_5d(st + x_bytes, &tmD, bar, c_base, c.w, c.z, p.f_first + c.y * p.f_step, c.x);
+        });
     }
-    __syncthreads();
-
     const int lanes = p.Gb * K;                         // (group, filter row) combinations
-    const int ppp = DWT_THREADS / lanes;
+    const int ppp = DWT_CONSUMERS / lanes;
     const int g = tid % p.Gb;
     const int i = (tid / p.Gb) % K;
-    const bool active = tid < ppp * lanes && (c_base + g * 4) < p.C;
+    const bool consumer = tid < DWT_CONSUMERS;
+    const bool active = consumer && tid < ppp * lanes && (c_base + g * 4) < p.C;
     const int slot = tid / lanes;
     float2 acc[K][2];
 #pragma unroll
     for (int t = 0; t < K; ++t) { acc[t][0] = make_float2(0.f, 0.f); acc[t][1] = make_float2(0.f, 0.f); }
-
-    const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int nstrips = p.Wt / WS;
     const int items = p.Ht * nstrips;
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t row_bytes = (uint32_t)(p.Wi * cb_bytes);
+    const uint32_t drow_bytes = (uint32_t)(p.Wt * cb_bytes);
+    const int lane = tid & 31;
 
-    auto issue = [&](long long n) {
-        TileCoord tc_ = decode_tile(p, blockIdx.x + n * (long long)gridDim.x);
-        const int s = (int)(n % p.stages);
-        mbar_expect_tx(&full_bar[s], (uint32_t)(p.box_bytes + p.box2_bytes));
-        uint8_t* st = ring + (size_t)s * p.stage_bytes;
-        tma_load_5d(st, &tmX, &full_bar[s], c_base, tc_.w0 * S - p.pS, tc_.h0 * S - p.pS,
-                    p.src_first + tc_.n * p.src_step, tc_.b);
-        tma_load_5d(st + x_bytes, &tmD, &full_bar[s], c_base, tc_.w0, tc_.h0, p.f_first + tc_.n * p.f_step, tc_.b);
-    };
-    if (tid == 0)
-        for (long long n = 0; n < my_tiles && n < p.stages; ++n) issue(n);
-
-    for (long long n = 0; n < my_tiles; ++n) {
-        const int s = (int)(n % p.stages);
-        mbar_wait(&full_bar[s], (uint32_t)((n / p.stages) & 1));
-        const uint8_t* xt = ring + (size_t)s * p.stage_bytes;
-        const uint8_t* dt = xt + x_bytes;
-        if (active) {
-            for (int it = slot; it < items; it += ppp) {
-                const int strip = it % nstrips, hl = it / nstrips;
-                const uint8_t* dp = dt + ((size_t)hl * p.Wt + (size_t)strip * WS) * cb_bytes + g * 8;
-                const uint8_t* xp = xt + ((size_t)(hl * S + i) * p.Wi + (size_t)strip * WS * S) * cb_bytes + g * 8;
-                float2 dyv[WS][2];
+    if (consumer) {
+        for (long long n = 0; n < my_tiles; ++n) {
+            const int s = (int)(n % p.stages);
+            mbar_wait(&cx.full[s], (uint32_t)((n / p.stages) & 1));
+            const uint32_t xt = ring_u32 + (uint32_t)(s * p.stage_bytes) + (uint32_t)(g * 8);
+            const uint32_t dt = xt + (uint32_t)x_bytes;
+            if (active) {
+                ItemIter it;
+                it.start(slot, ppp, nstrips);
+                for (int idx = slot; idx < items; idx += ppp, it.next()) {
+                    uint32_t da = dt + (uint32_t)it.hl * drow_bytes + (uint32_t)(it.strip * WS * cb_bytes);
+                    uint32_t xa = xt + (uint32_t)(it.hl * S + i) * row_bytes + (uint32_t)(it.strip * WS * S * cb_bytes);
+                    float2 dyv[WS][2];
 #pragma unroll
-                for (int o = 0; o < WS; ++o) {
-                    const uint2 u = *reinterpret_cast<const uint2*>(dp + (size_t)o * cb_bytes);
-                    dyv[o][0] = unpack2(u.x); dyv[o][1] = unpack2(u.y);
-                }
+                    for (int o = 0; o < WS; ++o, da += cb_bytes) {
+                        const uint2 u = lds64(da);
+                        dyv[o][0] = unpack2(u.x); dyv[o][1] = unpack2(u.y);
+                    }
 #pragma unroll
-                for (int j = 0; j < (WS - 1) * S + K; ++j) {
-                    const uint2 u = *reinterpret_cast<const uint2*>(xp + (size_t)j * cb_bytes);
-                    const float2 v0 = unpack2(u.x), v1 = unpack2(u.y);
+                    for (int j = 0; j < (WS - 1) * S + K; ++j, xa += cb_bytes) {
+                        const uint2 u = lds64(xa);
+                        const float2 v0 = unpack2(u.x), v1 = unpack2(u.y);
 #pragma unroll
-                    for (int o = 0; o < WS; ++o) {
-                        const int t = j - o * S;
-                        if (t >= 0 && t < K) {
-                            ffma2(acc[t][0], v0, dyv[o][0]);
-                            ffma2(acc[t][1], v1, dyv[o][1]);
+                        for (int o = 0; o < WS; ++o) {
+                            const int t = j - o * S;
+                            if (t >= 0 && t < K) {
+                                ffma2(acc[t][0], v0, dyv[o][0]);
+                                ffma2(acc[t][1], v1, dyv[o][1]);
+                            }
                         }
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cx.empty[s]);
         }
-        __syncthreads();
-        if (tid == 0 && n + p.stages < my_tiles) issue(n + p.stages);
     }
-
-    // reduce over the CTA's threads that share (g, i): shared-memory sums, then one atomic per (tap, channel)
+    // every issued tile has been consumed: the ring can be reused as scratch for the CTA-level reduction
+    __syncthreads();
     float* red = reinterpret_cast<float*>(ring);            // [K*K][Cb]
     for (int e = tid; e < K * K * p.Cb; e += DWT_THREADS) red[e] = 0.f;
     __syncthreads();
@@ -437,15 +478,14 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 struct PlanIn {
     int B, C;
-    int Ti, Hin, Win;      // staged tensor
-    int To, Ho, Wo;        // tiled tensor
-    int K, S, WS;          // S: source step per destination pixel (1 or 2); for dgrad-s2 pass S = 0 (half-rate)
+    int To, Ho, Wo;        // tiled (destination) tensor
+    int K, S, WS;          // S: source step per destination pixel (1 or 2); dgrad-s2 passes S = 0 (half-rate)
     int pS;
-    int extra_tile_bytes_per_pixel;   // wgrad: the dy tile adds Cb*2 bytes per destination pixel
+    int with_dst_tile;     // wgrad: the dy tile is staged too
 };
 
 static bool plan_tile(const PlanIn& in, DwTile& p) {
-    p.B = in.B; p.C = in.C; p.Ti = in.Ti; p.Hin = in.Hin; p.Win = in.Win; p.To = in.To; p.Ho = in.Ho; p.Wo = in.Wo;
+    p.B = in.B; p.C = in.C; p.To = in.To; p.Ho = in.Ho; p.Wo = in.Wo;
     p.pS = in.pS;
     p.nblk = ceil_div(in.C, 128);
     p.Cb = (ceil_div(in.C, p.nblk) + 7) / 8 * 8;
@@ -459,14 +499,12 @@ static bool plan_tile(const PlanIn& in, DwTile& p) {
     const int hstep = (S == 0) ? 2 : 1;
     double best_score = -1.0;
     int best_ht = 0, best_wt = 0;
-    for (int tw = 1; tw <= 16; ++tw) {
+    for (int tw = 1; tw <= 32; ++tw) {
         int wt = (ceil_div(in.Wo, tw) + WS - 1) / WS * WS;
-        if (tw > 1 && wt >= best_wt && best_wt > 0 && (ceil_div(in.Wo, tw - 1) + WS - 1) / WS * WS == wt) continue;
         int wi = src_extent(wt);
         if (wi > 256 || wt > 256) continue;
         for (int ht = hstep; ht <= in.Ho + hstep - 1; ht += hstep) {
-            long long bytes = (long long)src_extent(ht) * wi * p.Cb * 2 +
-                              (long long)in.extra_tile_bytes_per_pixel * ht * wt * p.Cb * 2;
+            long long bytes = (long long)src_extent(ht) * wi * p.Cb * 2 + (long long)in.with_dst_tile * ht * wt * p.Cb * 2;
             if (bytes > budget || src_extent(ht) > 256) break;
             int th = ceil_div(in.Ho, ht);
             int ht_bal = ceil_div(in.Ho, th);
@@ -478,7 +516,7 @@ static bool plan_tile(const PlanIn& in, DwTile& p) {
             double dest = (double)th * twn * ht * wt;
             if (S == 2) staged /= 4.0;                  // a stride-2 tile needs 4 source pixels per output anyway
             if (S == 0) staged *= 4.0;
-            double score = useful / std::max(staged, dest) + 1e-4 * std::min(bytes, (long long)budget) / budget;
+            double score = useful / std::max(staged, dest) + 1e-4 * (double)bytes / budget;
             if (score > best_score) { best_score = score; best_ht = ht; best_wt = wt; }
         }
     }
@@ -486,7 +524,7 @@ static bool plan_tile(const PlanIn& in, DwTile& p) {
     p.Wt = best_wt; p.tiles_w = ceil_div(in.Wo, best_wt); p.Wi = src_extent(best_wt);
     p.Ht = best_ht; p.tiles_h = ceil_div(in.Ho, best_ht); p.Hi = src_extent(best_ht);
     p.box_bytes = p.Hi * p.Wi * p.Cb * 2;
-    p.box2_bytes = in.extra_tile_bytes_per_pixel ? p.Ht * p.Wt * p.Cb * 2 : 0;
+    p.box2_bytes = in.with_dst_tile ? p.Ht * p.Wt * p.Cb * 2 : 0;
     p.stage_bytes = (p.box_bytes + 127) / 128 * 128 + (p.box2_bytes + 127) / 128 * 128;
     p.stages = std::min(DWT_MAX_STAGES, (108 * 1024) / p.stage_bytes);
     if (p.stages < 2) return false;
@@ -522,14 +560,14 @@ static bool plan_frames(DwTile& p, int n_dst, int n_src, int num, int off, int d
     p.f_step = step == 0 ? 1 : step;
     p.f_count = count;
     p.src_first = first < 0 ? 0 : (first * num + off) / den;
-    p.src_step = p.f_step * num / den;
     if (count > 1 && (p.f_step * num) % den != 0) return false;
+    p.src_step = p.f_step * num / den;
     p.ntiles = (long long)p.B * p.f_count * p.tiles_h * p.tiles_w;
     return true;
 }
 
 static dim3 persistent_grid(const DwTile& p) {
-    int ctas = std::max(1, ceil_div(148 * 2, p.nblk));
+    int ctas = std::max(1, (148 * 2) / p.nblk);           // never more than one resident wave
     ctas = (int)std::min<long long>(ctas, std::max<long long>(p.ntiles, 1));
     return dim3(ctas, p.nblk);
 }
@@ -543,7 +581,7 @@ template <int K, int S, int WS>
 static bool launch_fwd(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y, const DwDims& d, int pT, int sT,
                        int flip, cudaStream_t st) {
     DwTile p;
-    PlanIn in{d.B, d.C, d.T, d.H, d.W, d.To, d.Ho, d.Wo, K, S, WS, d.pH, 0};
+    PlanIn in{d.B, d.C, d.To, d.Ho, d.Wo, K, S, WS, d.pH, 0};
     if (!plan_tile(in, p)) return false;
     if (!plan_frames(p, d.To, d.T, sT, -pT, 1)) return false;      // source frame = to*sT - pT
     p.flip = flip;
@@ -560,7 +598,7 @@ static bool launch_dgrad_s2(const __nv_bfloat16* dy, const float* w_tc, __nv_bfl
                             cudaStream_t st) {
     constexpr int XS = 4;
     DwTile p;
-    PlanIn in{d.B, d.C, d.To, d.Ho, d.Wo, d.T, d.H, d.W, K, 0, XS, d.pH, 0};
+    PlanIn in{d.B, d.C, d.T, d.H, d.W, K, 0, XS, d.pH, 0};
     if (!plan_tile(in, p)) return false;
     if (!plan_frames(p, d.T, d.To, 1, d.pT, d.sT)) return false;   // source frame = (t + pT)/sT
     CUtensorMap tm;
@@ -575,9 +613,9 @@ template <int K, int S, int WS>
 static bool launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw_tc, const DwDims& d,
                          cudaStream_t st) {
     DwTile p;
-    PlanIn in{d.B, d.C, d.T, d.H, d.W, d.To, d.Ho, d.Wo, K, S, WS, d.pH, 1};
+    PlanIn in{d.B, d.C, d.To, d.Ho, d.Wo, K, S, WS, d.pH, 1};
     if (!plan_tile(in, p)) return false;
-    if (p.Gb * K > DWT_THREADS) return false;
+    if (p.Gb * K > DWT_CONSUMERS) return false;
     if (K * K * p.Cb * 4 > p.stages * p.stage_bytes) return false;
     if (!plan_frames(p, d.To, d.T, d.sT, -d.pT, 1)) return false;
     if (p.f_count == 0) return true;                                 // nothing contributes; dw stays zero
@@ -597,12 +635,16 @@ static bool mobilenet_class(const DwDims& d) {
 static bool aligned16(const void* a, const void* b) {
     return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
 }
+// strips of 7 fit the 112/56/28/14/7 widths of the 224x224 models exactly; 4 otherwise
+static bool strip7(int wo) { return wo % 7 == 0; }
 
 template <> bool dw_fwd_tiled<__nv_bfloat16>(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y,
                                             const DwDims& d, cudaStream_t st) {
     if (!mobilenet_class(d) || !aligned16(x, y)) return false;
-    if (d.kH == 3 && d.sH == 1) return launch_fwd<3, 1, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
-    if (d.kH == 3 && d.sH == 2) return launch_fwd<3, 2, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
+    if (d.kH == 3 && d.sH == 1)
+        return strip7(d.Wo) ? launch_fwd<3, 1, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st) : launch_fwd<3, 1, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
+    if (d.kH == 3 && d.sH == 2)
+        return strip7(d.Wo) ? launch_fwd<3, 2, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st) : launch_fwd<3, 2, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
     if (d.kH == 5 && d.sH == 1) return launch_fwd<5, 1, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
     if (d.kH == 5 && d.sH == 2) return launch_fwd<5, 2, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
     return false;
@@ -614,7 +656,6 @@ template <> bool dw_dgrad_tiled<__nv_bfloat16>(const __nv_bfloat16* dy, const fl
                                               const DwDims& d, cudaStream_t st) {
     if (!mobilenet_class(d) || !aligned16(dy, dx)) return false;
     if (d.sH == 2) {
-        if (d.sT != 1 && d.sT != 2) return false;
         if ((d.H | d.W) < 2) return false;
         return d.kH == 3 ? launch_dgrad_s2<3>(dy, w_tc, dx, d, st) : launch_dgrad_s2<5>(dy, w_tc, dx, d, st);
     }
@@ -622,15 +663,18 @@ template <> bool dw_dgrad_tiled<__nv_bfloat16>(const __nv_bfloat16* dy, const fl
     DwDims r = d;                      // roles swapped: "input" = dy (To,Ho,Wo), "output" = dx (T,H,W)
     r.T = d.To; r.H = d.Ho; r.W = d.Wo;
     r.To = d.T; r.Ho = d.H; r.Wo = d.W;
-    if (d.kH == 3) return launch_fwd<3, 1, 4>(dy, w_tc, dx, r, -d.pT, 1, 1, st);
+    if (d.kH == 3)
+        return strip7(r.Wo) ? launch_fwd<3, 1, 7>(dy, w_tc, dx, r, -d.pT, 1, 1, st) : launch_fwd<3, 1, 4>(dy, w_tc, dx, r, -d.pT, 1, 1, st);
     return launch_fwd<5, 1, 4>(dy, w_tc, dx, r, -d.pT, 1, 1, st);
 }
 
 template <> bool dw_wgrad_tiled<__nv_bfloat16>(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw_tc,
                                               const DwDims& d, cudaStream_t st) {
     if (!mobilenet_class(d) || !aligned16(x, dy)) return false;
-    if (d.kH == 3 && d.sH == 1) return launch_wgrad<3, 1, 4>(x, dy, dw_tc, d, st);
-    if (d.kH == 3 && d.sH == 2) return launch_wgrad<3, 2, 4>(x, dy, dw_tc, d, st);
+    if (d.kH == 3 && d.sH == 1)
+        return strip7(d.Wo) ? launch_wgrad<3, 1, 7>(x, dy, dw_tc, d, st) : launch_wgrad<3, 1, 4>(x, dy, dw_tc, d, st);
+    if (d.kH == 3 && d.sH == 2)
+        return strip7(d.Wo) ? launch_wgrad<3, 2, 7>(x, dy, dw_tc, d, st) : launch_wgrad<3, 2, 4>(x, dy, dw_tc, d, st);
     if (d.kH == 5 && d.sH == 1) return launch_wgrad<5, 1, 4>(x, dy, dw_tc, d, st);
     if (d.kH == 5 && d.sH == 2) return launch_wgrad<5, 2, 4>(x, dy, dw_tc, d, st);
     return false;
