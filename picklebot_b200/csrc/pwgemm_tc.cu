@@ -5,10 +5,13 @@
 //
 // Replaces nn.Conv3d(kernel_size=1) forward and input-gradient (mobilenet.py:64,79; movinet.py:47,63) for
 // bf16 activations.  These layers are HBM-bound (4-70 MAC/B): the design goal is to
-// stream A once at full bandwidth, so the kernel is persistent (one CTA per SM), keeps a 4-8 stage TMA
+// stream A once at full bandwidth, so the kernel is persistent (one CTA per SM), keeps a multi-stage TMA
 // ring in flight and double-buffers the accumulator in TMEM so the epilogue of tile i overlaps the MMAs
-// of tile i+1.  Tiles never straddle samples (3-D tensor maps), which lets the squeeze-excite gate be
-// folded into per-sample weights (Bw == Bt) and makes per-sample epilogue vectors trivial.
+// of tile i+1.  Skinny layers (K <= 64 and N <= 128: 16->16, 16->64, 24->72 ...) move only a few KB per
+// 128-row tile, so the fixed per-tile handshakes would dominate; there a tile spans `mt` (up to 4) stacked
+// 128-row sub-tiles that share one pipeline step and one accumulator hand-over.  Tiles never straddle
+// samples (3-D tensor maps), which lets the squeeze-excite gate be folded into per-sample weights
+// (Bw == Bt) and makes per-sample epilogue vectors trivial.
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
@@ -35,20 +38,28 @@ EncodeTiledFn encode_fn() {
 }
 
 constexpr int BM = 128, BK = 64;
-constexpr int A_STAGE_BYTES = BM * BK * 2;      // 16 KB
+constexpr int A_SUB_BYTES = BM * BK * 2;        // 16 KB per 128-row sub-tile
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 
 struct GemmParams {
     int Bt, K, N, Bw;
     long long R;
-    int block_n, n_tiles, m_tiles, k_chunks, stages;
+    int block_n, n_tiles, m_tiles, k_chunks, stages, mt;
     long long total_tiles;
     const float* bias;
     const float* colscale;
     const float* coladd;
     __nv_bfloat16* C;
 };
+
+__device__ __forceinline__ void ldg16(const float* p, float (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
+        v[q * 4 + 0] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+    }
+}
 
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmParams p) {
@@ -58,8 +69,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);      // 1024-byte aligned (SWIZZLE_128B)
-    const int w_stage_bytes = p.block_n * BK * 2;
-    const int stage_bytes = A_STAGE_BYTES + w_stage_bytes;
+    const int a_stage_bytes = p.mt * A_SUB_BYTES;
+    const int stage_bytes = a_stage_bytes + p.block_n * BK * 2;
+    const int acc_cols = p.mt * p.block_n;                              // TMEM columns per accumulator stage
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -79,15 +91,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
             for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                int n_tile = (int)(t % p.n_tiles);
-                long long mt = t / p.n_tiles;
-                int b = (int)(mt / p.m_tiles), m_tile = (int)(mt % p.m_tiles);
+                const int n_tile = (int)(t % p.n_tiles);
+                const long long mtile = t / p.n_tiles;
+                const int b = (int)(mtile / p.m_tiles), m_tile = (int)(mtile % p.m_tiles);
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
                     uint8_t* st = tiles + (size_t)s * stage_bytes;
-                    tma_load_3d(st, &tmA, &full_bar[s], kc * BK, m_tile * BM, b);
-                    tma_load_3d(st + A_STAGE_BYTES, &tmW, &full_bar[s], kc * BK, n_tile * p.block_n, p.Bw == 1 ? 0 : b);
+                    for (int sub = 0; sub < p.mt; ++sub)
+                        tma_load_3d(st + sub * A_SUB_BYTES, &tmA, &full_bar[s], kc * BK, (m_tile * p.mt + sub) * BM, b);
+                    tma_load_3d(st + a_stage_bytes, &tmW, &full_bar[s], kc * BK, n_tile * p.block_n, p.Bw == 1 ? 0 : b);
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -102,16 +115,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t aph = (uint32_t)((it >> 1) & 1);
                 mbar_wait(&tempty_bar[a], aph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.block_n);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * acc_cols);
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint64_t adesc = make_desc(sa, 16, 1024);
-                    const uint64_t bdesc = make_desc(sa + A_STAGE_BYTES, 16, 1024);
+                    const uint64_t bdesc = make_desc(sa + a_stage_bytes, 16, 1024);
+                    for (int sub = 0; sub < p.mt; ++sub) {
+                        const uint64_t adesc = make_desc(sa + sub * A_SUB_BYTES, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)      // UMMA_K = 16 bf16 = 32 bytes = 2 descriptor units
-                        umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes = 2 descriptor units
+                            umma_bf16(d_tmem + (uint32_t)(sub * p.block_n), adesc + (uint64_t)(2 * k),
+                                      bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
+                    }
                     umma_commit(&empty_bar[s]);             // frees the smem slot when these MMAs retire
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
@@ -124,47 +140,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int a = (int)(it & 1);
             const uint32_t aph = (uint32_t)((it >> 1) & 1);
-            int n_tile = (int)(t % p.n_tiles);
-            long long mt = t / p.n_tiles;
-            int b = (int)(mt / p.m_tiles), m_tile = (int)(mt % p.m_tiles);
+            const int n_tile = (int)(t % p.n_tiles);
+            const long long mtile = t / p.n_tiles;
+            const int b = (int)(mtile / p.m_tiles), m_tile = (int)(mtile % p.m_tiles);
+            const int n_base = n_tile * p.block_n;
+            const float* cs = p.colscale ? p.colscale + (long long)b * p.N : nullptr;
+            const float* ca = p.coladd ? p.coladd + (long long)b * p.N : nullptr;
             mbar_wait(&tfull_bar[a], aph);
             tc_fence_after();
-            const long long row = (long long)m_tile * BM + q * 32 + lane;
-            const bool row_ok = row < p.R;
-            __nv_bfloat16* crow = p.C + ((long long)b * p.R + row) * p.N;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.block_n);
-            const int n_base = n_tile * p.block_n;
-            for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + (uint32_t)c0, r);
-                tmem_ld_wait();
-                const int n0 = n_base + c0;
-                if (row_ok && n0 < p.N) {
-                    float v[16];
+            for (int sub = 0; sub < p.mt; ++sub) {
+                const long long row = ((long long)m_tile * p.mt + sub) * BM + q * 32 + lane;
+                const bool row_ok = row < p.R;
+                __nv_bfloat16* crow = p.C + ((long long)b * p.R + row) * p.N;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_cols + sub * p.block_n);
+                for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + (uint32_t)c0, r);
+                    tmem_ld_wait();
+                    const int n0 = n_base + c0;
+                    if (row_ok && n0 < p.N) {
+                        float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                    const int nv = min(16, p.N - n0);          // 8 or 16 (N % 8 == 0)
-                    if (p.bias) {
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                        const bool full16 = n0 + 16 <= p.N;        // else exactly 8 valid (N % 8 == 0)
+                        if (full16) {
+                            float e[16];
+                            if (p.bias) { ldg16(p.bias + n0, e);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) if (j < nv) v[j] += __ldg(p.bias + n0 + j);
+                                for (int j = 0; j < 16; ++j) v[j] += e[j]; }
+                            if (cs) { ldg16(cs + n0, e);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] *= e[j]; }
+                            if (ca) { ldg16(ca + n0, e);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] += e[j]; }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (p.bias) v[j] += __ldg(p.bias + n0 + j);
+                                if (cs) v[j] *= __ldg(cs + n0 + j);
+                                if (ca) v[j] += __ldg(ca + n0 + j);
+                            }
+                        }
+                        uint4 o0, o1;
+                        o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+                        o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+                        o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+                        o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+                        *reinterpret_cast<uint4*>(crow + n0) = o0;
+                        if (full16) *reinterpret_cast<uint4*>(crow + n0 + 8) = o1;
                     }
-                    if (p.colscale) {
-                        const float* cs = p.colscale + (long long)b * p.N + n0;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) if (j < nv) v[j] *= __ldg(cs + j);
-                    }
-                    if (p.coladd) {
-                        const float* ca = p.coladd + (long long)b * p.N + n0;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) if (j < nv) v[j] += __ldg(ca + j);
-                    }
-                    uint4 o0, o1;
-                    o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
-                    o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
-                    o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
-                    o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-                    *reinterpret_cast<uint4*>(crow + n0) = o0;
-                    if (nv > 8) *reinterpret_cast<uint4*>(crow + n0 + 8) = o1;
                 }
             }
             tc_fence_before();
@@ -193,15 +218,26 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     PB_REQUIRE(Bw == 1 || Bw == Bt, "pw_gemm_tc: Bw=%d must be 1 or Bt=%d", Bw, Bt);
     PB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W_bf16) & 15) == 0 &&
                (reinterpret_cast<uintptr_t>(C) & 15) == 0, "pw_gemm_tc: pointers must be 16-byte aligned");
+    PB_REQUIRE((!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
+               (!colscale || (reinterpret_cast<uintptr_t>(colscale) & 15) == 0) &&
+               (!coladd || (reinterpret_cast<uintptr_t>(coladd) & 15) == 0), "pw_gemm_tc: epilogue vectors must be 16-byte aligned");
+    PB_REQUIRE((!colscale && !coladd) || N % 4 == 0, "pw_gemm_tc: per-sample epilogue vectors need N %% 4 == 0");
     GemmParams p;
     p.Bt = Bt; p.K = K; p.N = N; p.Bw = Bw; p.R = R;
     p.n_tiles = ceil_div(N, 256);
     p.block_n = (ceil_div(N, p.n_tiles) + 15) / 16 * 16;
-    p.m_tiles = ceil_div(R, BM);
     p.k_chunks = ceil_div(K, BK);
+    // skinny layers: stack up to 4 sub-tiles of 128 rows per pipeline step
+    p.mt = 1;
+    if (p.k_chunks == 1 && p.n_tiles == 1) {
+        p.mt = std::min(4, 256 / p.block_n);
+        p.mt = (int)std::max<long long>(1, std::min<long long>(p.mt, (R + BM - 1) / BM));
+    }
+    p.m_tiles = ceil_div(R, (long long)BM * p.mt);
     p.total_tiles = (long long)Bt * p.m_tiles * p.n_tiles;
-    const int stage_bytes = A_STAGE_BYTES + p.block_n * BK * 2;
+    const int stage_bytes = p.mt * A_SUB_BYTES + p.block_n * BK * 2;
     p.stages = std::min(MAX_STAGES, (200 * 1024) / stage_bytes);
+    PB_REQUIRE(p.stages >= 2, "pw_gemm_tc: internal tiling error");
     p.bias = bias; p.colscale = colscale; p.coladd = coladd; p.C = (__nv_bfloat16*)C;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
 
@@ -221,7 +257,7 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);  // + static barriers <= 227 KB
+        attr_err = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(gemm_tc_kernel)");
     int dev = 0, sms = 148;
@@ -232,4 +268,3 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     PB_CHECK_LAUNCH("gemm_tc_kernel");
     return PB_OK;
 }
-

@@ -19,8 +19,8 @@
 namespace pb {
 namespace tc {
 
-constexpr int WG_ROWS = 64;                 // rows (reduction) per pipeline stage
-constexpr int WG_BOX_BYTES = WG_ROWS * 128; // one 64-row x 64-element bf16 box = 8 KB
+// rows (reduction) per pipeline stage: 64, or 128 for skinny layers (few boxes per stage) where the fixed
+// per-stage cost would otherwise dominate; one TMA box = rows x 64 bf16 elements (rows x 128 bytes)
 constexpr int WG_STAGES_MAX = 4;
 
 struct WgradPlan {
@@ -31,7 +31,9 @@ struct WgradPlan {
     int n_groups;
     int kw_boxes;    // ceil(KW / 64)
     int chunks;      // row chunks per batch entry
-    long long chunk_rows;   // multiple of WG_ROWS
+    long long chunk_rows;   // multiple of rows
+    int rows;               // reduction rows per stage (64 or 128)
+    int box_bytes;          // rows * 128
     int stages;
     int stage_bytes;
 };
@@ -46,13 +48,15 @@ static WgradPlan make_plan(int Bt, long long R, int K, int N) {
     p.per_group = std::max(1, std::min(p.NT, 512 / p.KW));
     p.per_group = std::max(1, std::min(p.per_group, (13 - p.kw_boxes) / 2));   // two stages must fit in 216 KB
     p.n_groups = ceil_div(p.NT, p.per_group);
-    p.stage_bytes = (p.per_group * 2 + p.kw_boxes) * WG_BOX_BYTES;
+    p.rows = (p.per_group * 2 + p.kw_boxes) <= 4 ? 128 : 64;
+    p.box_bytes = p.rows * 128;
+    p.stage_bytes = (p.per_group * 2 + p.kw_boxes) * p.box_bytes;
     p.stages = std::max(2, std::min(WG_STAGES_MAX, (216 * 1024) / p.stage_bytes));
     long long groups = (long long)p.k_groups * p.n_groups;
     long long want = std::max<long long>(1, (148LL * 2 + Bt * groups - 1) / (Bt * groups));
     long long max_chunks = std::max<long long>(1, R / 512);
     p.chunks = (int)std::min(want, max_chunks);
-    p.chunk_rows = ((R + p.chunks - 1) / p.chunks + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+    p.chunk_rows = ((R + p.chunks - 1) / p.chunks + p.rows - 1) / p.rows * p.rows;
     p.chunks = (int)((R + p.chunk_rows - 1) / p.chunk_rows);
     return p;
 }
@@ -82,8 +86,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
     const int k0 = kg * pl.KW;
     const long long r_begin = (long long)chunk * pl.chunk_rows;
     const long long r_end = min(p.R, r_begin + pl.chunk_rows);
-    const int iters = (int)((r_end - r_begin + WG_ROWS - 1) / WG_ROWS);
-    const int d_bytes = pl.per_group * 2 * WG_BOX_BYTES;   // dC part of a stage
+    const int iters = (int)((r_end - r_begin + pl.rows - 1) / pl.rows);
+    const int d_bytes = pl.per_group * 2 * pl.box_bytes;   // dC part of a stage
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmD);
@@ -101,16 +105,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            const uint32_t tx = (uint32_t)((ntiles * 2 + pl.kw_boxes) * WG_BOX_BYTES);
+            const uint32_t tx = (uint32_t)((ntiles * 2 + pl.kw_boxes) * pl.box_bytes);
             for (int it = 0; it < iters; ++it) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 mbar_expect_tx(&full_bar[s], tx);
                 uint8_t* st = tiles + (size_t)s * pl.stage_bytes;
-                const int r = (int)(r_begin + (long long)it * WG_ROWS);
+                const int r = (int)(r_begin + (long long)it * pl.rows);
                 for (int j = 0; j < ntiles * 2; ++j)
-                    tma_load_3d(st + j * WG_BOX_BYTES, &tmD, &full_bar[s], (nt0 * 2 + j) * 64, r, b);
+                    tma_load_3d(st + j * pl.box_bytes, &tmD, &full_bar[s], (nt0 * 2 + j) * 64, r, b);
                 for (int j = 0; j < pl.kw_boxes; ++j)
-                    tma_load_3d(st + d_bytes + j * WG_BOX_BYTES, &tmA, &full_bar[s], k0 + j * 64, r, b);
+                    tma_load_3d(st + d_bytes + j * pl.box_bytes, &tmA, &full_bar[s], k0 + j * 64, r, b);
                 if (++s == pl.stages) { s = 0; ph ^= 1; }
             }
         }
@@ -123,10 +127,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
                 tc_fence_after();
                 const uint32_t sb = smem_u32(tiles + (size_t)s * pl.stage_bytes);
                 for (int j = 0; j < ntiles; ++j) {
-#pragma unroll
-                    for (int ks = 0; ks < WG_ROWS / 16; ++ks) {     // 16 rows = 2 swizzle atoms = 2 KB
-                        const uint64_t adesc = make_desc(sb + j * 2 * WG_BOX_BYTES + ks * 2048, WG_BOX_BYTES, 1024);
-                        const uint64_t bdesc = make_desc(sb + d_bytes + ks * 2048, WG_BOX_BYTES, 1024);
+                    for (int ks = 0; ks < pl.rows / 16; ++ks) {     // 16 rows = 2 swizzle atoms = 2 KB
+                        const uint64_t adesc = make_desc(sb + j * 2 * pl.box_bytes + ks * 2048, pl.box_bytes, 1024);
+                        const uint64_t bdesc = make_desc(sb + d_bytes + ks * 2048, pl.box_bytes, 1024);
                         umma_bf16(tmem_base + (uint32_t)(j * pl.KW), adesc, bdesc, idesc, (it | ks) != 0);
                     }
                 }
@@ -232,13 +235,13 @@ extern "C" int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, 
     {
         uint64_t dims[3] = {(uint64_t)N, (uint64_t)R, (uint64_t)Bt};
         uint64_t str[3] = {2, (uint64_t)N * 2, (uint64_t)R * N * 2};
-        uint32_t box[3] = {64, WG_ROWS, 1};
+        uint32_t box[3] = {64, (uint32_t)pl.rows, 1};
         if (int e = make_tmap_bf16(&tmD, dC, 3, dims, str, box)) return e;
     }
     {
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)R, (uint64_t)Bt};
         uint64_t str[3] = {2, (uint64_t)K * 2, (uint64_t)R * K * 2};
-        uint32_t box[3] = {64, WG_ROWS, 1};
+        uint32_t box[3] = {64, (uint32_t)pl.rows, 1};
         if (int e = make_tmap_bf16(&tmA, A, 3, dims, str, box)) return e;
     }
     static std::once_flag attr_once;
