@@ -2,12 +2,12 @@
 //
 // The reduction runs over the rows m (up to 6.4 M), the output is tiny (N x K <= 960 x 160), so both MMA
 // operands are "MN-major": the row-major activations dC[m][n] and A[m][k] are exactly the transposes the MMA
-// needs, fetched by TMA as 64-row x 128-byte boxes (no transposes in HBM).  One CTA owns one group of
-// output tiles (up to 512 TMEM columns = 128 x 512 accumulators) and one chunk of rows; it streams its rows
-// once through a 3-stage TMA ring, then dumps the fp32 accumulators to a workspace slice.  A second,
-// small kernel sums the slices and, for squeeze-excite blocks, applies the gate per sample and produces
-// the gate gradient from the same per-sample products (so the backward pass never re-reads the expanded
-// activations for it):
+// needs, fetched by TMA as rows x 128-byte boxes (no transposes in HBM).  A work item is one group of output
+// tiles (up to 512 TMEM columns = 128 x 512 accumulators) times one chunk of rows; persistent CTAs (one per
+// SM) walk over the items, stream each item's rows once through a TMA ring, then dump the fp32 accumulators
+// to a workspace slice.  A second, small kernel sums the slices and, for squeeze-excite blocks, applies
+// the gate per sample and produces the gate gradient from the same per-sample products (so the backward
+// pass never re-reads the expanded activations for it):
 //     dW[n][k]    = sum_b gate[b][k] * P_b[n][k]
 //     dgate[b][k] = sum_n W[n][k]    * P_b[n][k]
 // Replaces the weight-gradient half of nn.Conv3d(kernel_size=1) autograd (train.py:269).
@@ -25,9 +25,9 @@ constexpr int WG_STAGES_MAX = 4;
 
 struct WgradPlan {
     int NT;          // 128-row output tiles along n
-    int KW;          // k-slice width per CTA (multiple of 16, <= 256)
+    int KW;          // k-slice width per item (multiple of 16, <= 256)
     int k_groups;    // slices along k
-    int per_group;   // n-tiles per CTA (per_group * KW <= 512)
+    int per_group;   // n-tiles per item (per_group * KW <= 512)
     int n_groups;
     int kw_boxes;    // ceil(KW / 64)
     int chunks;      // row chunks per batch entry
@@ -36,6 +36,7 @@ struct WgradPlan {
     int box_bytes;          // rows * 128
     int stages;
     int stage_bytes;
+    long long items;        // groups * chunks * Bt
 };
 
 static WgradPlan make_plan(int Bt, long long R, int K, int N) {
@@ -52,12 +53,14 @@ static WgradPlan make_plan(int Bt, long long R, int K, int N) {
     p.box_bytes = p.rows * 128;
     p.stage_bytes = (p.per_group * 2 + p.kw_boxes) * p.box_bytes;
     p.stages = std::max(2, std::min(WG_STAGES_MAX, (216 * 1024) / p.stage_bytes));
+    // aim at ~4 items per SM so the persistent CTAs stay balanced, but keep >= 1024 rows per item
     long long groups = (long long)p.k_groups * p.n_groups;
-    long long want = std::max<long long>(1, (148LL * 2 + Bt * groups - 1) / (Bt * groups));
-    long long max_chunks = std::max<long long>(1, R / 512);
+    long long want = std::max<long long>(1, (148LL * 4 + Bt * groups - 1) / (Bt * groups));
+    long long max_chunks = std::max<long long>(1, R / 1024);
     p.chunks = (int)std::min(want, max_chunks);
     p.chunk_rows = ((R + p.chunks - 1) / p.chunks + p.rows - 1) / p.rows * p.rows;
     p.chunks = (int)((R + p.chunk_rows - 1) / p.chunk_rows);
+    p.items = groups * p.chunks * Bt;
     return p;
 }
 
@@ -68,25 +71,27 @@ struct WgradParams {
     float* partial;     // [Bt][chunks][N][K]
 };
 
+struct WgItem { int kg, ng, chunk, b; };
+
+__device__ __forceinline__ WgItem decode_item(const WgradPlan& pl, long long it) {
+    WgItem w;
+    const int groups = pl.k_groups * pl.n_groups;
+    const int gidx = (int)(it % groups); it /= groups;
+    w.kg = gidx % pl.k_groups; w.ng = gidx / pl.k_groups;
+    w.chunk = (int)(it % pl.chunks);
+    w.b = (int)(it / pl.chunks);
+    return w;
+}
+
 __global__ void __launch_bounds__(256, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmA, WgradParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[WG_STAGES_MAX], empty_bar[WG_STAGES_MAX], done_bar;
+    __shared__ uint64_t full_bar[WG_STAGES_MAX], empty_bar[WG_STAGES_MAX], done_bar, tfree_bar;
     __shared__ uint32_t tmem_base_s;
     const WgradPlan& pl = p.plan;
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // blockIdx.x = group (k-slice fastest), blockIdx.y = chunk, blockIdx.z = batch entry
-    const int kg = blockIdx.x % pl.k_groups, ng = blockIdx.x / pl.k_groups;
-    const int chunk = blockIdx.y, b = blockIdx.z;
-    const int nt0 = ng * pl.per_group;
-    const int ntiles = min(pl.per_group, pl.NT - nt0);
-    const int k0 = kg * pl.KW;
-    const long long r_begin = (long long)chunk * pl.chunk_rows;
-    const long long r_end = min(p.R, r_begin + pl.chunk_rows);
-    const int iters = (int)((r_end - r_begin + pl.rows - 1) / pl.rows);
     const int d_bytes = pl.per_group * 2 * pl.box_bytes;   // dC part of a stage
 
     if (warp == 0 && lane == 0) {
@@ -94,6 +99,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
         tma_prefetch_desc(&tmA);
         for (int s = 0; s < pl.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&done_bar, 1);
+        mbar_init(&tfree_bar, 128);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(&tmem_base_s, 512);
@@ -105,68 +111,94 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            const uint32_t tx = (uint32_t)((ntiles * 2 + pl.kw_boxes) * pl.box_bytes);
-            for (int it = 0; it < iters; ++it) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], tx);
-                uint8_t* st = tiles + (size_t)s * pl.stage_bytes;
-                const int r = (int)(r_begin + (long long)it * pl.rows);
-                for (int j = 0; j < ntiles * 2; ++j)
-                    tma_load_3d(st + j * pl.box_bytes, &tmD, &full_bar[s], (nt0 * 2 + j) * 64, r, b);
-                for (int j = 0; j < pl.kw_boxes; ++j)
-                    tma_load_3d(st + d_bytes + j * pl.box_bytes, &tmA, &full_bar[s], k0 + j * 64, r, b);
-                if (++s == pl.stages) { s = 0; ph ^= 1; }
+            for (long long item = blockIdx.x; item < pl.items; item += gridDim.x) {
+                const WgItem w = decode_item(pl, item);
+                const int nt0 = w.ng * pl.per_group;
+                const int ntiles = min(pl.per_group, pl.NT - nt0);
+                const int k0 = w.kg * pl.KW;
+                const long long r_begin = (long long)w.chunk * pl.chunk_rows;
+                const long long r_end = min(p.R, r_begin + pl.chunk_rows);
+                const int iters = (int)((r_end - r_begin + pl.rows - 1) / pl.rows);
+                const uint32_t tx = (uint32_t)((ntiles * 2 + pl.kw_boxes) * pl.box_bytes);
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], tx);
+                    uint8_t* st = tiles + (size_t)s * pl.stage_bytes;
+                    const int r = (int)(r_begin + (long long)it * pl.rows);
+                    for (int j = 0; j < ntiles * 2; ++j)
+                        tma_load_3d(st + j * pl.box_bytes, &tmD, &full_bar[s], (nt0 * 2 + j) * 64, r, w.b);
+                    for (int j = 0; j < pl.kw_boxes; ++j)
+                        tma_load_3d(st + d_bytes + j * pl.box_bytes, &tmA, &full_bar[s], k0 + j * 64, r, w.b);
+                    if (++s == pl.stages) { s = 0; ph ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(128, pl.KW, 1, 1);
             int s = 0; uint32_t ph = 0;
-            for (int it = 0; it < iters; ++it) {
-                mbar_wait(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t sb = smem_u32(tiles + (size_t)s * pl.stage_bytes);
-                for (int j = 0; j < ntiles; ++j) {
-                    for (int ks = 0; ks < pl.rows / 16; ++ks) {     // 16 rows = 2 swizzle atoms = 2 KB
-                        const uint64_t adesc = make_desc(sb + j * 2 * pl.box_bytes + ks * 2048, pl.box_bytes, 1024);
-                        const uint64_t bdesc = make_desc(sb + d_bytes + ks * 2048, pl.box_bytes, 1024);
-                        umma_bf16(tmem_base + (uint32_t)(j * pl.KW), adesc, bdesc, idesc, (it | ks) != 0);
-                    }
+            uint32_t n_item = 0;
+            for (long long item = blockIdx.x; item < pl.items; item += gridDim.x, ++n_item) {
+                const WgItem w = decode_item(pl, item);
+                const int nt0 = w.ng * pl.per_group;
+                const int ntiles = min(pl.per_group, pl.NT - nt0);
+                const long long r_begin = (long long)w.chunk * pl.chunk_rows;
+                const long long r_end = min(p.R, r_begin + pl.chunk_rows);
+                const int iters = (int)((r_end - r_begin + pl.rows - 1) / pl.rows);
+                if (n_item > 0) {                       // the epilogue must have drained TMEM of the previous item
+                    mbar_wait(&tfree_bar, (n_item - 1) & 1);
+                    tc_fence_after();
                 }
-                umma_commit(&empty_bar[s]);
-                if (++s == pl.stages) { s = 0; ph ^= 1; }
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(tiles + (size_t)s * pl.stage_bytes);
+                    for (int j = 0; j < ntiles; ++j) {
+                        for (int ks = 0; ks < pl.rows / 16; ++ks) {     // 16 rows = 2 swizzle atoms = 2 KB
+                            const uint64_t adesc = make_desc(sb + j * 2 * pl.box_bytes + ks * 2048, pl.box_bytes, 1024);
+                            const uint64_t bdesc = make_desc(sb + d_bytes + ks * 2048, pl.box_bytes, 1024);
+                            umma_bf16(tmem_base + (uint32_t)(j * pl.KW), adesc, bdesc, idesc, (it | ks) != 0);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (++s == pl.stages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&done_bar);
             }
-            umma_commit(&done_bar);
         }
     } else if (warp >= 4) {
         const int q = warp & 3;
-        mbar_wait(&done_bar, 0);
-        tc_fence_after();
-        float* out = p.partial + ((long long)b * pl.chunks + chunk) * p.N * p.K;
-        for (int j = 0; j < ntiles; ++j) {
-            const int n = (nt0 + j) * 128 + q * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * pl.KW);
-            for (int c0 = 0; c0 < pl.KW; c0 += 16) {
-                uint32_t r[16];
-                if (iters > 0) {
+        uint32_t n_item = 0;
+        for (long long item = blockIdx.x; item < pl.items; item += gridDim.x, ++n_item) {
+            const WgItem w = decode_item(pl, item);
+            const int nt0 = w.ng * pl.per_group;
+            const int ntiles = min(pl.per_group, pl.NT - nt0);
+            const int k0 = w.kg * pl.KW;
+            mbar_wait(&done_bar, n_item & 1);
+            tc_fence_after();
+            float* out = p.partial + ((long long)w.b * pl.chunks + w.chunk) * p.N * p.K;
+            for (int j = 0; j < ntiles; ++j) {
+                const int n = (nt0 + j) * 128 + q * 32 + lane;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * pl.KW);
+                for (int c0 = 0; c0 < pl.KW; c0 += 16) {
+                    uint32_t r[16];
                     tmem_ld16(taddr + (uint32_t)c0, r);
                     tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = 0u;
-                }
-                const int k = k0 + c0;
-                if (n < p.N && k < p.K) {
-                    float* dst = out + (long long)n * p.K + k;
-                    const int nv = min(16, p.K - k);            // 8 or 16
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(r[0], r[1], r[2], r[3]);
-                    *reinterpret_cast<uint4*>(dst + 4) = make_uint4(r[4], r[5], r[6], r[7]);
-                    if (nv > 8) {
-                        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(r[8], r[9], r[10], r[11]);
-                        *reinterpret_cast<uint4*>(dst + 12) = make_uint4(r[12], r[13], r[14], r[15]);
+                    const int k = k0 + c0;
+                    if (n < p.N && k < p.K) {
+                        float* dst = out + (long long)n * p.K + k;
+                        const int nv = min(16, p.K - k);            // 8 or 16
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(r[0], r[1], r[2], r[3]);
+                        *reinterpret_cast<uint4*>(dst + 4) = make_uint4(r[4], r[5], r[6], r[7]);
+                        if (nv > 8) {
+                            *reinterpret_cast<uint4*>(dst + 8) = make_uint4(r[8], r[9], r[10], r[11]);
+                            *reinterpret_cast<uint4*>(dst + 12) = make_uint4(r[12], r[13], r[14], r[15]);
+                        }
                     }
                 }
             }
+            tc_fence_before();
+            mbar_arrive(&tfree_bar);
         }
     }
     tc_fence_before();
@@ -230,7 +262,6 @@ extern "C" int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, 
     p.plan = make_plan(Bt, R, K, N);
     p.partial = (float*)workspace;
     const WgradPlan& pl = p.plan;
-    PB_REQUIRE(pl.chunks <= 65535, "pw_wgrad_tc: too many row chunks");
     CUtensorMap tmD, tmA;
     {
         uint64_t dims[3] = {(uint64_t)N, (uint64_t)R, (uint64_t)Bt};
@@ -251,7 +282,10 @@ extern "C" int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, 
     });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_tc_kernel)");
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(pl.k_groups * pl.n_groups, pl.chunks, Bt);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)std::min<long long>(pl.items, sms);
     const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024;
     wgrad_tc_kernel<<<grid, 256, smem, st>>>(tmD, tmA, p);
     PB_CHECK_LAUNCH("wgrad_tc_kernel");

@@ -1,10 +1,13 @@
 // Column reductions over NDHWC matrices X[nbatch][R][C]: every thread owns 8 channels and strides over
-// rows; fp32 per-thread partials -> shared-memory atomics per CTA -> one global atomic per (value,
-// channel) per CTA (fp64 for BatchNorm statistics, fp32 for pooling).
+// rows (4 rows in flight per iteration to cover HBM latency); fp32 per-thread partials -> shared-memory
+// atomics per CTA -> one global atomic per (value, channel) per CTA (fp64 for BatchNorm statistics, fp32
+// for pooling).
 #pragma once
 #include "common.cuh"
 
 namespace pb {
+
+constexpr int COLRED_UNROLL = 2;
 
 // F: struct with  __device__ void operator()(int batch, long long row_in_batch, int c0, float (&out)[NV][8]) const
 template <typename F, int NV, typename OUT>
@@ -24,7 +27,20 @@ colreduce_kernel(F f, long long R, int C, OUT* __restrict__ out, int nbatch, flo
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
         const int c0 = g << 3;
-        for (long long r = (long long)blockIdx.x * RPI + rr; r < R; r += (long long)gridDim.x * RPI) {
+        const long long stride = (long long)gridDim.x * RPI;
+        long long r = (long long)blockIdx.x * RPI + rr;
+        for (; r + (COLRED_UNROLL - 1) * stride < R; r += COLRED_UNROLL * stride) {
+            float t[COLRED_UNROLL][NV][8];
+#pragma unroll
+            for (int u = 0; u < COLRED_UNROLL; ++u) f(b, r + u * stride, c0, t[u]);
+#pragma unroll
+            for (int u = 0; u < COLRED_UNROLL; ++u)
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[v][i] += t[u][v][i];
+        }
+        for (; r < R; r += stride) {
             float t[NV][8];
             f(b, r, c0, t);
 #pragma unroll

@@ -1,0 +1,171 @@
+// Squeeze-excite fully connected layers (SEBlock3D.se[1], se[3]; mobilenet.py:17-20) for a batch of pooled
+// vectors: tiny GEMMs (B = 64 samples, C <= 960, C/4 hidden units) that must not cost a kernel per sample.
+//   hidden = relu(W1 mean + b1)            [B][Ch]
+//   gate   = hardsigmoid(W2 hidden + b2)   [B][C]
+// and their backward.  Two kernel shapes cover everything:
+//   fc_rows: W stored [N][K] (outputs are rows): one warp per output, lanes stride over K, BT samples per CTA
+//   fc_cols: W stored [K][N] (outputs are columns): one thread per output, sequential over K
+#include "common.cuh"
+
+namespace pb {
+
+constexpr int FC_BT = 16;      // samples per CTA
+
+// Y[b][n] = act(bias[n] + sum_k X[b][k] * W[n][k]) ; optional elementwise mask multiplies the result
+template <int ACT>
+__global__ void __launch_bounds__(256)
+fc_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
+               float* __restrict__ Y, int B, int N, int K) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + warp;
+    const int b0 = blockIdx.y * FC_BT;
+    if (n >= N) return;
+    float acc[FC_BT];
+#pragma unroll
+    for (int i = 0; i < FC_BT; ++i) acc[i] = 0.f;
+    const float* w = W + (long long)n * K;
+    for (int k = lane; k < K; k += 32) {
+        const float wv = __ldg(w + k);
+#pragma unroll
+        for (int i = 0; i < FC_BT; ++i) {
+            const int b = b0 + i;
+            if (b < B) acc[i] = fmaf(__ldg(X + (long long)b * K + k), wv, acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < FC_BT; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+        const float bv = bias ? bias[n] : 0.f;
+#pragma unroll
+        for (int i = 0; i < FC_BT; ++i) {
+            const int b = b0 + i;
+            if (b < B) Y[(long long)b * N + n] = act_fwd(acc[i] + bv, ACT, 0.f);
+        }
+    }
+}
+
+// Y[b][n] = scale * sum_k X[b][k] * Wt[k][n], optionally masked by (relu_ref[b][n] > 0)  (relu backward).
+// blockDim = (32 outputs, 8 k-slices): coalesced weight reads along n, K split over the 8 slices, then a
+// shared-memory reduction over the slices.
+__global__ void __launch_bounds__(256)
+fc_cols_kernel(const float* __restrict__ X, const float* __restrict__ Wt, const float* __restrict__ relu_ref,
+               float* __restrict__ Y, int B, int N, int K, float scale) {
+    __shared__ float red[8][FC_BT][33];
+    const int nl = threadIdx.x & 31, ks = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + nl;
+    const int b0 = blockIdx.y * FC_BT;
+    float acc[FC_BT];
+#pragma unroll
+    for (int i = 0; i < FC_BT; ++i) acc[i] = 0.f;
+    if (n < N) {
+        for (int k = ks; k < K; k += 8) {
+            const float wv = __ldg(Wt + (long long)k * N + n);
+#pragma unroll
+            for (int i = 0; i < FC_BT; ++i) {
+                const int b = b0 + i;
+                if (b < B) acc[i] = fmaf(__ldg(X + (long long)b * K + k), wv, acc[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < FC_BT; ++i) red[ks][i][nl] = acc[i];
+    __syncthreads();
+    // thread (nl, ks) finishes samples ks and ks+8
+#pragma unroll
+    for (int h = 0; h < FC_BT / 8; ++h) {
+        const int i = ks + h * 8;
+        const int b = b0 + i;
+        if (n < N && b < B) {
+            float v = 0.f;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) v += red[s][i][nl];
+            v *= scale;
+            if (relu_ref && !(relu_ref[(long long)b * N + n] > 0.f)) v = 0.f;
+            Y[(long long)b * N + n] = v;
+        }
+    }
+}
+
+// da2 = dgate * hardsigmoid'(.) : 1/6 where 0 < gate < 1
+__global__ void hsig_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
+                                float* __restrict__ da2, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = gate[i];
+    da2[i] = (g > 0.f && g < 1.f) ? dgate[i] * (1.f / 6.f) : 0.f;
+}
+
+// parameter gradients: sums over the B samples
+__global__ void se_fc_bwd_param_kernel(const float* __restrict__ a2, const float* __restrict__ a1,
+                                       const float* __restrict__ mean, const float* __restrict__ hidden,
+                                       float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
+                                       float* __restrict__ db2, int B, int C, int Ch) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long nW = (long long)C * Ch;
+    if (idx < nW) {                       // dW2[c][j] = sum_b da2[b][c] * hidden[b][j]
+        int c = (int)(idx / Ch), j = (int)(idx % Ch);
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s = fmaf(a2[(long long)b * C + c], hidden[(long long)b * Ch + j], s);
+        dW2[idx] = s;
+    } else if (idx < 2 * nW) {            // dW1[j][c] = sum_b da1[b][j] * mean[b][c]
+        long long i = idx - nW;
+        int j = (int)(i / C), c = (int)(i % C);
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s = fmaf(a1[(long long)b * Ch + j], mean[(long long)b * C + c], s);
+        dW1[i] = s;
+    } else if (idx < 2 * nW + C) {
+        int c = (int)(idx - 2 * nW);
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += a2[(long long)b * C + c];
+        db2[c] = s;
+    } else if (idx < 2 * nW + C + Ch) {
+        int j = (int)(idx - 2 * nW - C);
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += a1[(long long)b * Ch + j];
+        db1[j] = s;
+    }
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" int pb_se_fc_fwd(const float* mean, const float* W1, const float* b1, const float* W2, const float* b2,
+                            float* hidden, float* gate, int B, int C, int Ch, pb_stream_t stream) {
+    PB_REQUIRE(mean && W1 && b1 && W2 && b2 && hidden && gate && B > 0 && C > 0 && Ch > 0, "se_fc_fwd: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 g1(ceil_div(Ch, 8), ceil_div(B, FC_BT));
+    fc_rows_kernel<PB_ACT_RELU><<<g1, 256, 0, st>>>(mean, W1, b1, hidden, B, Ch, C);
+    PB_CHECK_LAUNCH("se_fc_fwd(1)");
+    dim3 g2(ceil_div(C, 8), ceil_div(B, FC_BT));
+    fc_rows_kernel<PB_ACT_HSIGMOID><<<g2, 256, 0, st>>>(hidden, W2, b2, gate, B, C, Ch);
+    PB_CHECK_LAUNCH("se_fc_fwd(2)");
+    return PB_OK;
+}
+
+extern "C" int pb_se_fc_bwd(const float* dgate, const float* mean, const float* hidden, const float* gate,
+                            const float* W1, const float* W2, float inv_R, float* dmean, float* work,
+                            float* dW1, float* db1, float* dW2, float* db2, int B, int C, int Ch,
+                            pb_stream_t stream) {
+    PB_REQUIRE(dgate && mean && hidden && gate && W1 && W2 && dmean && work && dW1 && db1 && dW2 && db2,
+               "se_fc_bwd: null pointer");
+    PB_REQUIRE(B > 0 && C > 0 && Ch > 0, "se_fc_bwd: bad dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* a2 = work;                          // [B][C]
+    float* a1 = work + (long long)B * C;       // [B][Ch]
+    const long long nBC = (long long)B * C;
+    hsig_bwd_kernel<<<ceil_div(nBC, 256), 256, 0, st>>>(dgate, gate, a2, nBC);
+    PB_CHECK_LAUNCH("se_fc_bwd(hsig)");
+    // da1[b][j] = relu'(hidden) * sum_c da2[b][c] * W2[c][j]   (W2 is [C][Ch] = "Wt" with K=C, N=Ch)
+    dim3 g1(ceil_div(Ch, 32), ceil_div(B, FC_BT));
+    fc_cols_kernel<<<g1, 256, 0, st>>>(a2, W2, hidden, a1, B, Ch, C, 1.f);
+    PB_CHECK_LAUNCH("se_fc_bwd(da1)");
+    // dmean[b][c] = inv_R * sum_j da1[b][j] * W1[j][c]         (W1 is [Ch][C] = "Wt" with K=Ch, N=C)
+    dim3 g2(ceil_div(C, 32), ceil_div(B, FC_BT));
+    fc_cols_kernel<<<g2, 256, 0, st>>>(a1, W1, nullptr, dmean, B, C, Ch, inv_R);
+    PB_CHECK_LAUNCH("se_fc_bwd(dmean)");
+    long long n = 2LL * C * Ch + C + Ch;
+    se_fc_bwd_param_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a2, a1, mean, hidden, dW1, db1, dW2, db2, B, C, Ch);
+    PB_CHECK_LAUNCH("se_fc_bwd(param)");
+    return PB_OK;
+}
