@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=1)
+    ap.add_argument("--dp", default="buckets", choices=["buckets", "ddp"],
+                    help="gradient exchange for N>1: picklebot_b200.dp.GradientBuckets or torch DDP")
     return ap.parse_args()
 
 
@@ -177,6 +179,11 @@ def main():
     import picklebot_b200 as pb
     from picklebot_b200 import _lib, synth
 
+    # stdout carries exactly ONE JSON line: library chatter (e.g. "NCCL version ...") goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -193,8 +200,14 @@ def main():
     model.load_state_dict(synth.synthetic_state_dict(model.state_dict()))
     model = model.to(dev).train()
     net = model
+    buckets = None
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+        if args.dp == "ddp":
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+        else:
+            from picklebot_b200 import dp as pbdp
+            pbdp.broadcast_module(model)
+            buckets = pbdp.GradientBuckets(model.parameters())
     opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=5e-4, fused=True)
 
     # synthetic uint8 clips: this rank's shard of each global batch, distinct per micro-batch
@@ -207,10 +220,12 @@ def main():
             logits = net(x_u8.permute(0, 4, 1, 2, 3))        # (B,3,T,H,W) view of the uint8 NTHWC batch
             loss = F.cross_entropy(logits.float(), y) / accum
         if world > 1 and not sync_grads:
-            with net.no_sync():
+            with (buckets.no_sync() if buckets is not None else net.no_sync()):
                 loss.backward()
         else:
             loss.backward()
+            if buckets is not None:
+                buckets.finish()            # wait for the bucketed all-reduces, averaged grads back in .grad
         return loss.detach()
 
     def step_resident():
@@ -351,13 +366,20 @@ def main():
             "config": {"workload": "MobileNetLarge3D training step, bf16 autocast, synthetic uint8 clips 3x16x224x224 "
                                    "(BASELINE.json configs[2])",
                        "global_batch": args.global_batch, "micro_batch_per_gpu": micro, "accum_steps": accum,
-                       "parallelism": f"dp{world}", "optimizer": "torch.optim.AdamW(fused=True) inside the timed region",
+                       "parallelism": f"dp{world}",
+                       "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                             "picklebot_b200.dp.GradientBuckets: bucketed async NCCL all-reduce from "
+                                             "post-accumulate-grad hooks, once per optimizer step" if args.dp == "buckets"
+                                             else "torch DDP, no_sync on all but the last micro-batch"),
+"optimizer": "torch.optim.AdamW(fused=True) inside the timed region",
                        "l2": "inputs larger than L2 (154 MB uint8 per micro-batch, distinct buffers); no flush",
                        "num_classes": NUM_CLASSES},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
