@@ -209,33 +209,47 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
     }
 }
 
-// dW[n][k] = sum_b gate[b][k] * sum_c partial[b][c][n][k]; leaves P_b in partial[b][0] when chunks > 1
-__global__ void wgrad_reduce_kernel(float* __restrict__ partial, const float* __restrict__ gate,
-                                    float* __restrict__ dW, int Bt, int chunks, int N, int K) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// dW[n][k] = sum_b gate[b][k] * sum_c partial[b][c][n][k].
+// blockDim = (32 outputs, 8 slices of the Bt*chunks partial list): a skinny layer can have ~600 partials of a
+// few hundred floats, so the sum over partials is parallel too; shared-memory reduction over the slices.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ gate,
+                    float* __restrict__ dW, int Bt, int chunks, int N, int K) {
+    __shared__ float red[8][33];
+    const int ol = threadIdx.x & 31, ps = threadIdx.x >> 5;
     const long long NK = (long long)N * K;
-    if (idx >= NK) return;
-    const int k = (int)(idx % K);
+    const long long idx = (long long)blockIdx.x * 32 + ol;
+    const int P = Bt * chunks;
     float acc = 0.f;
-    for (int b = 0; b < Bt; ++b) {
-        float* pb = partial + (long long)b * chunks * NK + idx;
-        float s = pb[0];
-        for (int c = 1; c < chunks; ++c) s += pb[(long long)c * NK];
-        if (chunks > 1 && gate) pb[0] = s;
-        acc = gate ? fmaf(gate[(long long)b * K + k], s, acc) : acc + s;
+    if (idx < NK) {
+        const int k = (int)(idx % K);
+        for (int q = ps; q < P; q += 8) {
+            const float v = partial[(long long)q * NK + idx];
+            acc = gate ? fmaf(gate[(long long)(q / chunks) * K + k], v, acc) : acc + v;
+        }
     }
-    dW[idx] = acc;
+    red[ps][ol] = acc;
+    __syncthreads();
+    if (ps == 0 && idx < NK) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][ol];
+        dW[idx] = s;
+    }
 }
 
-// dgate[b][k] = sum_n W[n][k] * P_b[n][k]
+// dgate[b][k] = sum_n W[n][k] * P_b[n][k],  P_b = sum_c partial[b][c]
 __global__ void wgrad_dgate_kernel(const float* __restrict__ partial, const float* __restrict__ W,
                                    float* __restrict__ dgate, int Bt, int chunks, int N, int K) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (k >= K) return;
-    const float* pb = partial + (long long)b * chunks * N * K;
+    const long long NK = (long long)N * K;
     float acc = 0.f;
-    for (int n = 0; n < N; ++n) acc = fmaf(W[(long long)n * K + k], pb[(long long)n * K + k], acc);
+    for (int c = 0; c < chunks; ++c) {
+        const float* pb = partial + ((long long)b * chunks + c) * NK;
+        for (int n = 0; n < N; ++n) acc = fmaf(W[(long long)n * K + k], pb[(long long)n * K + k], acc);
+    }
     dgate[(long long)b * K + k] = acc;
 }
 
@@ -290,7 +304,7 @@ extern "C" int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, 
     wgrad_tc_kernel<<<grid, 256, smem, st>>>(tmD, tmA, p);
     PB_CHECK_LAUNCH("wgrad_tc_kernel");
     const long long NK = (long long)N * K;
-    wgrad_reduce_kernel<<<ceil_div(NK, 256), 256, 0, st>>>(p.partial, gate, dW, Bt, pl.chunks, N, K);
+    wgrad_reduce_kernel<<<ceil_div(NK, 32), 256, 0, st>>>(p.partial, gate, dW, Bt, pl.chunks, N, K);
     PB_CHECK_LAUNCH("wgrad_reduce_kernel");
     if (dgate) {
         dim3 g2(ceil_div(K, 128), Bt);
