@@ -255,11 +255,13 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(max(3, args.warmup)):
-        step_resident()
+    # the clock sampler starts with the warm-up (nvidia-smi needs ~0.5 s to deliver its first line) and runs
+    # through the timed region: every sample is taken under the same load
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step_resident()
     n0 = _lib.launch_count()
     ms = timed(step_resident, args.steps)
     launches = _lib.launch_count() - n0

@@ -536,7 +536,7 @@ static int make_map5(CUtensorMap* tm, const void* base, int C, int W, int H, int
     uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)B};
     uint64_t str[5] = {2, (uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)T * H * W * C * 2};
     uint32_t box[5] = {(uint32_t)bc, (uint32_t)bw, (uint32_t)bh, 1, 1};
-    return make_tmap_bf16(tm, base, 5, dims, str, box, false);
+    return make_tmap_bf16(tm, base, 5, dims, str, box, 0);
 }
 
 // frame bookkeeping: destination frame f has source frame  (f*num + off)/den  when divisible and in range

@@ -1,6 +1,12 @@
 // BatchNorm (train/eval) + activation + Dropout3d mask, forward and backward, on NDHWC matrices.
 // Replaces nn.BatchNorm3d / BatchNorm1d, nn.Hardswish / ReLU / LeakyReLU and nn.Dropout3d call sites
 // (mobilenet.py:80-82,90-92,142-143,180-181,247-248; movinet.py:65,75-76,93,141-143,150-152).
+//
+// All row-streaming kernels share one thread layout: a thread owns 8 fixed channels (so the per-channel
+// constants live in registers for the whole kernel) and walks over rows with a CTA-wide stride; the
+// activation is a template parameter, index math is 32-bit.
+#include <algorithm>
+
 #include "reduce.cuh"
 
 namespace pb {
@@ -48,65 +54,163 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double M, co
     if (invstd_o) invstd_o[c] = invstd;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-bn_act_fwd_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
-                  const float* __restrict__ mask, T* __restrict__ out, long long R, int C, int act, float slope,
-                  long long total) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int G = C >> 3;
-    int c0 = (int)(idx % G) << 3;
-    long long m = idx / G;
-    F8 v = load8(z + idx * 8);
-    float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
-    float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c0)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
-    float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-    F8 o;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o.v[i] = act_fwd(fmaf(v.v[i], sc[i], sh[i]), act, slope);
-    if (mask) {
-        const float* mp = mask + (m / R) * C + c0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] *= __ldg(mp + i);
+template <int ACT> __device__ __forceinline__ float actf(float u, float slope) { return act_fwd(u, ACT, slope); }
+template <int ACT> __device__ __forceinline__ float actg(float u, float slope) { return act_grad(u, ACT, slope); }
+
+struct RowLayout {
+    int G, RPI, g, rr, c0;
+    bool active;
+    __device__ __forceinline__ RowLayout(int C) {
+        G = C >> 3; RPI = blockDim.x / G;
+        g = threadIdx.x % G; rr = threadIdx.x / G; c0 = g << 3;
+        active = rr < RPI;
     }
-    store8(out + idx * 8, o);
+};
+
+__device__ __forceinline__ void load_vec8(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// du = dout * mask * act'(u), u = z*scale + shift, xhat = (z - mean) * invstd
-template <typename T>
-struct BnBwdCommon {
-    const void* dout; int dout_bcast; const T* z;
-    const float *scale, *shift, *mean, *invstd, *mask;
-    long long R; int C; int act; float slope;
-    __device__ __forceinline__ void eval(long long m, int c0, float (&du)[8], float (&xh)[8]) const {
-        long long b = m / R;
-        F8 zv = load8(z + m * C + c0);
-        F8 dv;
-        if (dout_bcast) dv = load8(reinterpret_cast<const float*>(dout) + b * C + c0);
-        else            dv = load8(reinterpret_cast<const T*>(dout) + m * C + c0);
+// out = act(z*scale + shift) * mask[b][c]
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                  const float* __restrict__ mask, T* __restrict__ out, unsigned M, unsigned R, int C, float slope) {
+    const RowLayout L(C);
+    if (!L.active) return;
+    float sc[8], sh[8];
+    load_vec8(scale + L.c0, sc);
+    load_vec8(shift + L.c0, sh);
+    const unsigned stride = gridDim.x * L.RPI;
+    for (unsigned m = blockIdx.x * L.RPI + L.rr; m < M; m += stride) {
+        const size_t o = (size_t)m * C + L.c0;
+        F8 v = load8(z + o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v.v[i] = actf<ACT>(fmaf(v.v[i], sc[i], sh[i]), slope);
+        if (mask) {
+            float mk[8];
+            load_vec8(mask + (size_t)(m / R) * C + L.c0, mk);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v.v[i] *= mk[i];
+        }
+        store8(out + o, v);
+    }
+}
+
+// du = dout * mask * act'(u), u = z*scale + shift, xhat = z*a + bb with a = invstd, bb = -mean*invstd
+template <typename T, int ACT, bool BCAST>
+__device__ __forceinline__ void bn_bwd_elem(const void* dout, const T* z, const float* mask, unsigned m, unsigned R,
+                                            int C, int c0, const float (&sc)[8], const float (&sh)[8],
+                                            const float (&a)[8], const float (&bb)[8], float slope,
+                                            float (&du)[8], float (&xh)[8]) {
+    const size_t o = (size_t)m * C + c0;
+    const F8 zv = load8(z + o);
+    F8 dv;
+    const unsigned b = (BCAST || mask) ? m / R : 0;
+    if (BCAST) dv = load8(reinterpret_cast<const float*>(dout) + (size_t)b * C + c0);
+    else       dv = load8(reinterpret_cast<const T*>(dout) + o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float u = fmaf(zv.v[i], sc[i], sh[i]);
+        du[i] = dv.v[i] * actg<ACT>(u, slope);
+        xh[i] = fmaf(zv.v[i], a[i], bb[i]);
+    }
+    if (mask) {
+        float mk[8];
+        load_vec8(mask + (size_t)b * C + c0, mk);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) du[i] *= mk[i];
+    }
+}
+
+// pass 1: sums[0][c] = sum du, sums[1][c] = sum du*xhat
+template <typename T, int ACT, bool BCAST>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const void* __restrict__ dout, const T* __restrict__ z, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, const float* __restrict__ mask, double* __restrict__ sums,
+                     unsigned M, unsigned R, int C, float slope) {
+    extern __shared__ float sm_red[];   // [2][C]
+    const RowLayout L(C);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm_red[i] = 0.f;
+    __syncthreads();
+    if (L.active) {
+        float sc[8], sh[8], a[8], bb[8];
+        load_vec8(scale + L.c0, sc);
+        load_vec8(shift + L.c0, sh);
+        load_vec8(invstd + L.c0, a);
+        load_vec8(mean + L.c0, bb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bb[i] = -bb[i] * a[i];
+        float s0[8], s1[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+        const unsigned stride = gridDim.x * L.RPI;
+        unsigned m = blockIdx.x * L.RPI + L.rr;
+        for (; m + stride < M; m += 2 * stride) {           // two rows in flight
+            float d0[8], x0[8], d1[8], x1[8];
+            bn_bwd_elem<T, ACT, BCAST>(dout, z, mask, m, R, C, L.c0, sc, sh, a, bb, slope, d0, x0);
+            bn_bwd_elem<T, ACT, BCAST>(dout, z, mask, m + stride, R, C, L.c0, sc, sh, a, bb, slope, d1, x1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s0[i] += d0[i] + d1[i];
+                s1[i] = fmaf(d0[i], x0[i], fmaf(d1[i], x1[i], s1[i]));
+            }
+        }
+        if (m < M) {
+            float d0[8], x0[8];
+            bn_bwd_elem<T, ACT, BCAST>(dout, z, mask, m, R, C, L.c0, sc, sh, a, bb, slope, d0, x0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s0[i] += d0[i]; s1[i] = fmaf(d0[i], x0[i], s1[i]); }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float u = fmaf(zv.v[i], scale[c0 + i], shift[c0 + i]);
-            float g = dv.v[i] * act_grad(u, act, slope);
-            if (mask) g *= mask[b * C + c0 + i];
-            du[i] = g;
-            xh[i] = (zv.v[i] - mean[c0 + i]) * invstd[c0 + i];
+            atomicAdd(&sm_red[L.c0 + i], s0[i]);
+            atomicAdd(&sm_red[C + L.c0 + i], s1[i]);
         }
     }
-};
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)sm_red[i]);
+}
 
+// batch statistics: sums[0][c] = sum z, sums[1][c] = sum z^2 (four rows in flight per thread)
 template <typename T>
-struct BnBwdReduceF {
-    BnBwdCommon<T> k;
-    __device__ void operator()(int, long long r, int c0, float (&out)[2][8]) const {
-        float du[8], xh[8];
-        k.eval(r, c0, du, xh);
+__global__ void __launch_bounds__(256)
+colstats_kernel(const T* __restrict__ z, double* __restrict__ sums, unsigned M, int C) {
+    extern __shared__ float sm_red[];   // [2][C]
+    const RowLayout L(C);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm_red[i] = 0.f;
+    __syncthreads();
+    if (L.active) {
+        float s0[8], s1[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { out[0][i] = du[i]; out[1][i] = du[i] * xh[i]; }
+        for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+        const unsigned stride = gridDim.x * L.RPI;
+        unsigned m = blockIdx.x * L.RPI + L.rr;
+        for (; m + 3 * stride < M; m += 4 * stride) {
+            F8 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = load8(z + (size_t)(m + u * stride) * C + L.c0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s0[i] += v[u].v[i]; s1[i] = fmaf(v[u].v[i], v[u].v[i], s1[i]); }
+        }
+        for (; m < M; m += stride) {
+            const F8 v = load8(z + (size_t)m * C + L.c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s0[i] += v.v[i]; s1[i] = fmaf(v.v[i], v.v[i], s1[i]); }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            atomicAdd(&sm_red[L.c0 + i], s0[i]);
+            atomicAdd(&sm_red[C + L.c0 + i], s1[i]);
+        }
     }
-};
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)sm_red[i]);
+}
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double M, int training,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -120,35 +224,67 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double M
     coef[C + c] = training ? (float)(s1 / M) : 0.f;
 }
 
-template <typename T>
+// pass 2: dz = scale * (du - coef0 - xhat*coef1)
+template <typename T, int ACT, bool BCAST>
 __global__ void __launch_bounds__(256)
-bn_act_bwd_apply_kernel(BnBwdCommon<T> k, const float* __restrict__ coef, T* __restrict__ dz, long long total) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int G = k.C >> 3;
-    int c0 = (int)(idx % G) << 3;
-    long long m = idx / G;
-    float du[8], xh[8];
-    k.eval(m, c0, du, xh);
-    F8 o;
+bn_bwd_apply_kernel(const void* __restrict__ dout, const T* __restrict__ z, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ mask,
+                    const float* __restrict__ coef, T* __restrict__ dz, unsigned M, unsigned R, int C, float slope) {
+    const RowLayout L(C);
+    if (!L.active) return;
+    float sc[8], sh[8], a[8], bb[8], k0[8], k1[8];
+    load_vec8(scale + L.c0, sc);
+    load_vec8(shift + L.c0, sh);
+    load_vec8(invstd + L.c0, a);
+    load_vec8(mean + L.c0, bb);
+    load_vec8(coef + L.c0, k0);
+    load_vec8(coef + C + L.c0, k1);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-        o.v[i] = k.scale[c0 + i] * (du[i] - coef[c0 + i] - xh[i] * coef[k.C + c0 + i]);
-    store8(dz + idx * 8, o);
+    for (int i = 0; i < 8; ++i) bb[i] = -bb[i] * a[i];
+    const unsigned stride = gridDim.x * L.RPI;
+    for (unsigned m = blockIdx.x * L.RPI + L.rr; m < M; m += stride) {
+        float du[8], xh[8];
+        bn_bwd_elem<T, ACT, BCAST>(dout, z, mask, m, R, C, L.c0, sc, sh, a, bb, slope, du, xh);
+        F8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = sc[i] * (du[i] - k0[i] - xh[i] * k1[i]);
+        store8(dz + (size_t)m * C + L.c0, o);
+    }
+}
+
+static inline int row_grid(long long M, int C) {
+    int G = C >> 3, RPI = 256 / G;
+    long long max_ctas = (M + (long long)RPI * 8 - 1) / ((long long)RPI * 8);   // >= 8 rows per thread: few atomics
+    long long want = 148LL * 8;
+    return (int)std::max<long long>(1, std::min(max_ctas, want));
 }
 
 }  // namespace pb
 
 using namespace pb;
 
+// Dispatch on the activation code; body sees the compile-time constant ACT.
+#define PB_DISPATCH_ACT(act, ...)                                                      \
+    do {                                                                               \
+        switch (act) {                                                                 \
+            case PB_ACT_NONE:     { constexpr int ACT = PB_ACT_NONE; __VA_ARGS__; } break;     \
+            case PB_ACT_RELU:     { constexpr int ACT = PB_ACT_RELU; __VA_ARGS__; } break;     \
+            case PB_ACT_HSWISH:   { constexpr int ACT = PB_ACT_HSWISH; __VA_ARGS__; } break;   \
+            case PB_ACT_LRELU:    { constexpr int ACT = PB_ACT_LRELU; __VA_ARGS__; } break;    \
+            case PB_ACT_HSIGMOID: { constexpr int ACT = PB_ACT_HSIGMOID; __VA_ARGS__; } break; \
+            default: pb::set_error("unknown activation %d", (int)(act)); return PB_ERR_BAD_ARG; \
+        }                                                                              \
+    } while (0)
+
 extern "C" int pb_colstats(const void* x, int dtype, long long M, int C, double* sums, pb_stream_t stream) {
     PB_REQUIRE(x && sums && M > 0 && C > 0 && C % 8 == 0 && C <= 2048, "colstats: bad args (M=%lld C=%d)", M, C);
     cudaStream_t st = (cudaStream_t)stream;
     PB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
-    dim3 grid = colreduce_grid(M, C, 1);
+    PB_REQUIRE(M < (1LL << 31), "colstats: too many rows");
+    const int grid = row_grid(M, C);
     PB_DISPATCH_DTYPE(dtype, {
-        StatsF<T> f{(const T*)x, M, C};
-        colreduce_kernel<StatsF<T>, 2, double><<<grid, 256, sizeof(float) * 2 * C, st>>>(f, M, C, sums, 1, 1.f);
+        colstats_kernel<T><<<grid, 256, sizeof(float) * 2 * C, st>>>((const T*)x, sums, (unsigned)M, C);
     });
     PB_CHECK_LAUNCH("colstats");
     return PB_OK;
@@ -168,12 +304,14 @@ extern "C" int pb_bn_finalize(const double* sums, long long M, const float* gamm
 
 extern "C" int pb_bn_act_fwd(const void* z, const float* scale, const float* shift, const float* mask, void* out,
                              int dtype, int B, long long R, int C, int act, float slope, pb_stream_t stream) {
-    PB_REQUIRE(z && scale && shift && out && B > 0 && R > 0 && C > 0 && C % 8 == 0, "bn_act_fwd: bad args");
-    long long total = (long long)B * R * (C / 8);
-    PB_DISPATCH_DTYPE(dtype, {
-        bn_act_fwd_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)z, scale, shift, mask,
-                                                                                  (T*)out, R, C, act, slope, total);
-    });
+    PB_REQUIRE(z && scale && shift && out && B > 0 && R > 0 && C > 0 && C % 8 == 0 && C <= 2048, "bn_act_fwd: bad args");
+    const long long M = (long long)B * R;
+    PB_REQUIRE(M < (1LL << 31) && R < (1LL << 31), "bn_act_fwd: too many rows");
+    const int grid = row_grid(M, C);
+    PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
+        bn_act_fwd_kernel<T, ACT><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)z, scale, shift, mask, (T*)out,
+                                                                        (unsigned)M, (unsigned)R, C, slope);
+    }));
     PB_CHECK_LAUNCH("bn_act_fwd");
     return PB_OK;
 }
@@ -184,14 +322,20 @@ extern "C" int pb_bn_act_bwd_reduce(const void* dout, int dout_bcast, const void
                                     pb_stream_t stream) {
     PB_REQUIRE(dout && z && scale && shift && mean && invstd && sums, "bn_act_bwd_reduce: null pointer");
     PB_REQUIRE(B > 0 && R > 0 && C > 0 && C % 8 == 0 && C <= 2048, "bn_act_bwd_reduce: bad dims");
+    const long long M = (long long)B * R;
+    PB_REQUIRE(M < (1LL << 31) && R < (1LL << 31), "bn_act_bwd_reduce: too many rows");
     cudaStream_t st = (cudaStream_t)stream;
     PB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
-    long long M = (long long)B * R;
-    dim3 grid = colreduce_grid(M, C, 1);
-    PB_DISPATCH_DTYPE(dtype, {
-        BnBwdReduceF<T> f{{dout, dout_bcast, (const T*)z, scale, shift, mean, invstd, mask, R, C, act, slope}};
-        colreduce_kernel<BnBwdReduceF<T>, 2, double><<<grid, 256, sizeof(float) * 2 * C, st>>>(f, M, C, sums, 1, 1.f);
-    });
+    const int grid = row_grid(M, C);
+    const size_t smem = sizeof(float) * 2 * C;
+    PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
+        if (dout_bcast)
+            bn_bwd_reduce_kernel<T, ACT, true><<<grid, 256, smem, st>>>(dout, (const T*)z, scale, shift, mean, invstd,
+                                                                      mask, sums, (unsigned)M, (unsigned)R, C, slope);
+        else
+            bn_bwd_reduce_kernel<T, ACT, false><<<grid, 256, smem, st>>>(dout, (const T*)z, scale, shift, mean, invstd,
+                                                                       mask, sums, (unsigned)M, (unsigned)R, C, slope);
+    }));
     PB_CHECK_LAUNCH("bn_act_bwd_reduce");
     return PB_OK;
 }
@@ -209,12 +353,19 @@ extern "C" int pb_bn_act_bwd_apply(const void* dout, int dout_bcast, const void*
                                    const float* coef, void* dz, int dtype, int B, long long R, int C, int act,
                                    float slope, pb_stream_t stream) {
     PB_REQUIRE(dout && z && scale && shift && mean && invstd && coef && dz, "bn_act_bwd_apply: null pointer");
-    PB_REQUIRE(B > 0 && R > 0 && C > 0 && C % 8 == 0, "bn_act_bwd_apply: bad dims");
-    long long total = (long long)B * R * (C / 8);
-    PB_DISPATCH_DTYPE(dtype, {
-        BnBwdCommon<T> k{dout, dout_bcast, (const T*)z, scale, shift, mean, invstd, mask, R, C, act, slope};
-        bn_act_bwd_apply_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(k, coef, (T*)dz, total);
-    });
+    PB_REQUIRE(B > 0 && R > 0 && C > 0 && C % 8 == 0 && C <= 2048, "bn_act_bwd_apply: bad dims");
+    const long long M = (long long)B * R;
+    PB_REQUIRE(M < (1LL << 31) && R < (1LL << 31), "bn_act_bwd_apply: too many rows");
+    const int grid = row_grid(M, C);
+    cudaStream_t st = (cudaStream_t)stream;
+    PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
+        if (dout_bcast)
+            bn_bwd_apply_kernel<T, ACT, true><<<grid, 256, 0, st>>>(dout, (const T*)z, scale, shift, mean, invstd, mask,
+                                                                  coef, (T*)dz, (unsigned)M, (unsigned)R, C, slope);
+        else
+            bn_bwd_apply_kernel<T, ACT, false><<<grid, 256, 0, st>>>(dout, (const T*)z, scale, shift, mean, invstd, mask,
+                                                                   coef, (T*)dz, (unsigned)M, (unsigned)R, C, slope);
+    }));
     PB_CHECK_LAUNCH("bn_act_bwd_apply");
     return PB_OK;
 }

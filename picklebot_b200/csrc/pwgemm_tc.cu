@@ -13,8 +13,8 @@
 // samples (3-D tensor maps), which lets the squeeze-excite gate be folded into per-sample weights
 // (Bw == Bt) and makes per-sample epilogue vectors trivial.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 and 8-11 = two epilogue groups, one per accumulator stage (warp w owns TMEM lanes 32*(w%4)..+31).
 #include <algorithm>
 #include <mutex>
 
@@ -37,8 +37,7 @@ EncodeTiledFn encode_fn() {
     return g_encode;
 }
 
-constexpr int BM = 128, BK = 64;
-constexpr int A_SUB_BYTES = BM * BK * 2;        // 16 KB per 128-row sub-tile
+constexpr int BM = 128;
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 
@@ -46,6 +45,7 @@ struct GemmParams {
     int Bt, K, N, Bw;
     long long R;
     int block_n, n_tiles, m_tiles, k_chunks, stages, mt;
+    int bk;            // K elements per chunk = swizzle span / 2: 64 (128B), 32 (64B) or 16 (32B rows) for tiny K
     long long total_tiles;
     const float* bias;
     const float* colscale;
@@ -61,7 +61,7 @@ __device__ __forceinline__ void ldg16(const float* p, float (&v)[16]) {
     }
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
@@ -69,8 +69,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);      // 1024-byte aligned (SWIZZLE_128B)
+    const int BK = p.bk;
+    const int pitch = BK * 2;                                           // bytes per smem row = swizzle span
+    const int A_SUB_BYTES = BM * pitch;                                 // one 128-row sub-tile
+    const uint32_t layout = pitch == 128 ? 2u : pitch == 64 ? 4u : 6u;  // UMMA layout type of the swizzle mode
     const int a_stage_bytes = p.mt * A_SUB_BYTES;
-    const int stage_bytes = a_stage_bytes + p.block_n * BK * 2;
+    const int stage_bytes = a_stage_bytes + p.block_n * pitch;
     const int acc_cols = p.mt * p.block_n;                              // TMEM columns per accumulator stage
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -120,10 +124,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint64_t bdesc = make_desc(sa + a_stage_bytes, 16, 1024);
+                    const uint64_t bdesc = make_desc(sa + a_stage_bytes, 16, 8 * pitch, layout);
                     for (int sub = 0; sub < p.mt; ++sub) {
-                        const uint64_t adesc = make_desc(sa + sub * A_SUB_BYTES, 16, 1024);
-#pragma unroll
+                        const uint64_t adesc = make_desc(sa + sub * A_SUB_BYTES, 16, 8 * pitch, layout);
                         for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes = 2 descriptor units
                             umma_bf16(d_tmem + (uint32_t)(sub * p.block_n), adesc + (uint64_t)(2 * k),
                                       bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
@@ -135,10 +138,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp >= 4) {
+        // two epilogue warpgroups (warps 4-7 and 8-11): group g drains accumulator stage g, i.e. every other
+        // tile, so the TMEM loads / conversions / stores of consecutive tiles overlap
         const int q = warp & 3;
+        const int group = (warp - 4) >> 2;
         long long it = 0;
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int a = (int)(it & 1);
+            if (a != group) continue;
             const uint32_t aph = (uint32_t)((it >> 1) & 1);
             const int n_tile = (int)(t % p.n_tiles);
             const long long mtile = t / p.n_tiles;
@@ -226,16 +233,19 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     p.Bt = Bt; p.K = K; p.N = N; p.Bw = Bw; p.R = R;
     p.n_tiles = ceil_div(N, 256);
     p.block_n = (ceil_div(N, p.n_tiles) + 15) / 16 * 16;
+    p.bk = K <= 16 ? 16 : (K <= 32 ? 32 : 64);
+    const int BK = p.bk;
     p.k_chunks = ceil_div(K, BK);
     // skinny layers: stack up to 4 sub-tiles of 128 rows per pipeline step
     p.mt = 1;
-    if (p.k_chunks == 1 && p.n_tiles == 1) {
+    if (p.n_tiles == 1 && p.k_chunks <= 4) {
         p.mt = std::min(4, 256 / p.block_n);
         p.mt = (int)std::max<long long>(1, std::min<long long>(p.mt, (R + BM - 1) / BM));
+        while (p.mt > 1 && (200 * 1024) / ((p.mt * BM + p.block_n) * BK * 2) < 3) --p.mt;   // keep >= 3 stages
     }
     p.m_tiles = ceil_div(R, (long long)BM * p.mt);
     p.total_tiles = (long long)Bt * p.m_tiles * p.n_tiles;
-    const int stage_bytes = p.mt * A_SUB_BYTES + p.block_n * BK * 2;
+    const int stage_bytes = (p.mt * BM + p.block_n) * BK * 2;
     p.stages = std::min(MAX_STAGES, (200 * 1024) / stage_bytes);
     PB_REQUIRE(p.stages >= 2, "pw_gemm_tc: internal tiling error");
     p.bias = bias; p.colscale = colscale; p.coladd = coladd; p.C = (__nv_bfloat16*)C;
@@ -245,14 +255,14 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     {
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)R, (uint64_t)Bt};
         uint64_t str[3] = {2, (uint64_t)K * 2, (uint64_t)R * K * 2};
-        uint32_t box[3] = {BK, BM, 1};
-        if (int e = make_tmap_bf16(&tmA, A, 3, dims, str, box)) return e;
+        uint32_t box[3] = {(uint32_t)BK, BM, 1};
+        if (int e = make_tmap_bf16(&tmA, A, 3, dims, str, box, BK * 2)) return e;
     }
     {
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)Bw};
         uint64_t str[3] = {2, (uint64_t)K * 2, (uint64_t)N * K * 2};
-        uint32_t box[3] = {BK, (uint32_t)p.block_n, 1};
-        if (int e = make_tmap_bf16(&tmW, W_bf16, 3, dims, str, box)) return e;
+        uint32_t box[3] = {(uint32_t)BK, (uint32_t)p.block_n, 1};
+        if (int e = make_tmap_bf16(&tmW, W_bf16, 3, dims, str, box, BK * 2)) return e;
     }
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
@@ -264,7 +274,7 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = (int)std::min<long long>(p.total_tiles, sms);
-    gemm_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
+    gemm_tc_kernel<<<grid, 384, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
     PB_CHECK_LAUNCH("gemm_tc_kernel");
     return PB_OK;
 }

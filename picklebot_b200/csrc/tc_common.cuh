@@ -22,14 +22,16 @@ EncodeTiledFn encode_fn();   // defined in pwgemm_tc.cu; nullptr if the driver l
 // bf16 tensor, up to 3 dims (innermost first), 128-byte swizzle, zero fill out of bounds.
 // dims[i] / strides_bytes[i] (stride of dim i, i >= 1) / box[i].
 static inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
-                                 const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128 = true) {
+                                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled unavailable in this driver"); return PB_ERR_UNSUPPORTED; }
     cuuint64_t gdim[5]; cuuint64_t gstr[5] = {0, 0, 0, 0, 0}; cuuint32_t bx[5]; cuuint32_t es[5];
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i + 1];
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B :
+                    swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -138,13 +140,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   K-major : rows of 64 elements (128 B); 8-row groups 1024 B apart (SBO); LBO unused.
 //   MN-major: 64 MN-elements (128 B) per k-row; 8 k-rows per 1024 B atom (SBO = 1024); 64-element MN
 //             blocks `lbo_bytes` apart.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                             uint32_t layout_type = 2 /* 2 = SWIZZLE_128B, 4 = 64B, 6 = 32B */) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;     // version = 1 (Blackwell)
-    d |= (uint64_t)2 << 61;     // SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 // kind::f16 instruction descriptor (InstrDescriptor): bf16 x bf16 -> fp32
