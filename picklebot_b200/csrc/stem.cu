@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "stem_tc.cuh"
 
 namespace pb {
 
@@ -182,6 +183,18 @@ static int stem_check(const StemDims& d) {
     return PB_OK;
 }
 
+// tcgen05 path (stem_tc.cu): bf16 activations, RGB channels-last clip, 3x3 spatial kernel, 16 output channels
+static bool stem_tc_eligible(const StemDims& d, int y_dtype) {
+    return y_dtype == PB_BF16 && d.Cin == 3 && d.Cout == STEM_COUT && d.kH == 3 && d.kW == 3 && (d.kT == 3 || d.kT == 1) &&
+           d.xs_c == 1 && d.xs_w == 3;
+}
+static StemTc stem_tc_dims(const StemDims& d) {
+    StemTc t{d.B, d.T, d.H, d.W, d.To, d.Ho, d.Wo, d.sT, d.sH, d.sW, d.pT, d.pH, d.pW, d.xs_b, d.xs_t, d.xs_h, 0, 0};
+    t.P = (long long)d.B * d.To * d.Ho * d.Wo;
+    t.steps = (t.P + 255) / 256;
+    return t;
+}
+
 }  // namespace pb
 
 using namespace pb;
@@ -215,6 +228,10 @@ extern "C" int pb_stem_conv_fwd(const void* x, int x_dtype, STEM_ARGS, const flo
     STEM_PACK;
     if (int e = stem_check(d)) return e;
     PB_REQUIRE(x && w && y, "stem_conv_fwd: null pointer");
+    if (stem_tc_eligible(d, y_dtype) && stem_tc_fwd(x, x_dtype, w, bias, y, kT, stem_tc_dims(d), (cudaStream_t)stream)) {
+        PB_CHECK_LAUNCH("stem_tc_fwd_kernel");
+        return PB_OK;
+    }
     long long P = (long long)B * To * Ho * Wo;
     size_t smem = sizeof(float) * ((size_t)kT * kH * kW * Cin * STEM_COUT + 256);
     STEM_DISPATCH(x_dtype, y_dtype, {
@@ -233,6 +250,10 @@ extern "C" int pb_stem_conv_wgrad(const void* x, int x_dtype, STEM_ARGS, const v
     const int taps = kT * kH * kW;
     PB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * taps, st));
     if (dbias) PB_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, st));
+    if (stem_tc_eligible(d, y_dtype) && stem_tc_wgrad(x, x_dtype, dy, dw, dbias, kT, stem_tc_dims(d), st)) {
+        PB_CHECK_LAUNCH("stem_tc_wgrad_kernel");
+        return PB_OK;
+    }
     long long P = (long long)B * To * Ho * Wo;
     long long per = std::max<long long>(STEM_TP, (P + 148 * 8 - 1) / (148 * 8));
     per = (per + STEM_TP - 1) / STEM_TP * STEM_TP;
