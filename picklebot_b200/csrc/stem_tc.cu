@@ -111,7 +111,7 @@ __device__ __forceinline__ void gather_row(const TX* __restrict__ x, const StemT
 // forward
 // ------------------------------------------------------------------------------------------------
 template <typename TX, int KT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 stem_tc_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                    __nv_bfloat16* __restrict__ y, const StemTc d) {
     constexpr int NK = KT * 27;
@@ -205,7 +205,7 @@ stem_tc_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ w, const 
 // weight (and bias) gradient
 // ------------------------------------------------------------------------------------------------
 template <typename TX, int KT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 stem_tc_wgrad_kernel(const TX* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ dw,
                      float* __restrict__ dbias, const StemTc d) {
     constexpr int NK = KT * 27;
@@ -298,7 +298,7 @@ static int stc_grid(const StemTc& d) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return (int)std::min<long long>(d.steps, sms);
+    return (int)std::min<long long>(d.steps, 2LL * sms);      // two CTAs per SM hide the gather latency
 }
 
 // Both return true if they launched; false = shape not covered (caller uses the direct kernels).
