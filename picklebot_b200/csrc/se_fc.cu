@@ -9,51 +9,72 @@
 
 namespace pb {
 
-constexpr int FC_BT = 16;      // samples per CTA
+constexpr int FC_BT = 8;       // samples per CTA; their input vectors are staged in shared memory
 
-// Y[b][n] = act(bias[n] + sum_k X[b][k] * W[n][k]) ; optional elementwise mask multiplies the result
+__device__ __forceinline__ void stage_x(const float* __restrict__ X, float* xs, int b0, int B, int K) {
+    for (int i = threadIdx.x; i < FC_BT * K; i += blockDim.x) {
+        const int bi = i / K, k = i - bi * K;
+        xs[i] = (b0 + bi < B) ? __ldg(X + (long long)(b0 + bi) * K + k) : 0.f;
+    }
+    __syncthreads();
+}
+
+// Y[b][n] = act(bias[n] + sum_k X[b][k] * W[n][k]).  CTA = 32 outputs x FC_BT samples; a warp owns 4 outputs,
+// lanes stride over K (coalesced weight rows, conflict-free shared-memory reads of X).
 template <int ACT>
 __global__ void __launch_bounds__(256)
 fc_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
                float* __restrict__ Y, int B, int N, int K) {
+    extern __shared__ float xs[];                       // [FC_BT][K]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * 8 + warp;
     const int b0 = blockIdx.y * FC_BT;
-    if (n >= N) return;
-    float acc[FC_BT];
+    stage_x(X, xs, b0, B, K);
+    const int n0 = blockIdx.x * 32 + warp * 4;
+    float acc[4][FC_BT];
 #pragma unroll
-    for (int i = 0; i < FC_BT; ++i) acc[i] = 0.f;
-    const float* w = W + (long long)n * K;
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < FC_BT; ++i) acc[j][i] = 0.f;
     for (int k = lane; k < K; k += 32) {
-        const float wv = __ldg(w + k);
+        float wv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wv[j] = (n0 + j < N) ? __ldg(W + (long long)(n0 + j) * K + k) : 0.f;
 #pragma unroll
         for (int i = 0; i < FC_BT; ++i) {
-            const int b = b0 + i;
-            if (b < B) acc[i] = fmaf(__ldg(X + (long long)b * K + k), wv, acc[i]);
+            const float xv = xs[i * K + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(xv, wv[j], acc[j][i]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < FC_BT; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane == 0) {
-        const float bv = bias ? bias[n] : 0.f;
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int i = 0; i < FC_BT; ++i) {
-            const int b = b0 + i;
-            if (b < B) Y[(long long)b * N + n] = act_fwd(acc[i] + bv, ACT, 0.f);
+        for (int i = 0; i < FC_BT; ++i) acc[j][i] = warp_sum(acc[j][i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + j;
+            if (n >= N) continue;
+            const float bv = bias ? bias[n] : 0.f;
+#pragma unroll
+            for (int i = 0; i < FC_BT; ++i)
+                if (b0 + i < B) Y[(long long)(b0 + i) * N + n] = act_fwd(acc[j][i] + bv, ACT, 0.f);
         }
     }
 }
 
 // Y[b][n] = scale * sum_k X[b][k] * Wt[k][n], optionally masked by (relu_ref[b][n] > 0)  (relu backward).
-// blockDim = (32 outputs, 8 k-slices): coalesced weight reads along n, K split over the 8 slices, then a
-// shared-memory reduction over the slices.
+// blockDim = (32 outputs, 8 k-slices): coalesced weight reads along n, X broadcast from shared memory, K split
+// over the 8 slices, then a shared-memory reduction over the slices.
 __global__ void __launch_bounds__(256)
 fc_cols_kernel(const float* __restrict__ X, const float* __restrict__ Wt, const float* __restrict__ relu_ref,
                float* __restrict__ Y, int B, int N, int K, float scale) {
-    __shared__ float red[8][FC_BT][33];
+    extern __shared__ float xs[];                       // [FC_BT][K] | red[8][FC_BT][33]
+    float* red = xs + FC_BT * K;
     const int nl = threadIdx.x & 31, ks = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + nl;
     const int b0 = blockIdx.y * FC_BT;
+    stage_x(X, xs, b0, B, K);
     float acc[FC_BT];
 #pragma unroll
     for (int i = 0; i < FC_BT; ++i) acc[i] = 0.f;
@@ -61,24 +82,18 @@ fc_cols_kernel(const float* __restrict__ X, const float* __restrict__ Wt, const 
         for (int k = ks; k < K; k += 8) {
             const float wv = __ldg(Wt + (long long)k * N + n);
 #pragma unroll
-            for (int i = 0; i < FC_BT; ++i) {
-                const int b = b0 + i;
-                if (b < B) acc[i] = fmaf(__ldg(X + (long long)b * K + k), wv, acc[i]);
-            }
+            for (int i = 0; i < FC_BT; ++i) acc[i] = fmaf(xs[i * K + k], wv, acc[i]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < FC_BT; ++i) red[ks][i][nl] = acc[i];
+    for (int i = 0; i < FC_BT; ++i) red[(ks * FC_BT + i) * 33 + nl] = acc[i];
     __syncthreads();
-    // thread (nl, ks) finishes samples ks and ks+8
-#pragma unroll
-    for (int h = 0; h < FC_BT / 8; ++h) {
-        const int i = ks + h * 8;
-        const int b = b0 + i;
-        if (n < N && b < B) {
+    {   // thread (nl, ks) finishes sample ks
+        const int i = ks, b = b0 + i;
+        if (i < FC_BT && n < N && b < B) {
             float v = 0.f;
 #pragma unroll
-            for (int s = 0; s < 8; ++s) v += red[s][i][nl];
+            for (int s2 = 0; s2 < 8; ++s2) v += red[(s2 * FC_BT + i) * 33 + nl];
             v *= scale;
             if (relu_ref && !(relu_ref[(long long)b * N + n] > 0.f)) v = 0.f;
             Y[(long long)b * N + n] = v;
@@ -134,11 +149,12 @@ extern "C" int pb_se_fc_fwd(const float* mean, const float* W1, const float* b1,
                             float* hidden, float* gate, int B, int C, int Ch, pb_stream_t stream) {
     PB_REQUIRE(mean && W1 && b1 && W2 && b2 && hidden && gate && B > 0 && C > 0 && Ch > 0, "se_fc_fwd: bad args");
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 g1(ceil_div(Ch, 8), ceil_div(B, FC_BT));
-    fc_rows_kernel<PB_ACT_RELU><<<g1, 256, 0, st>>>(mean, W1, b1, hidden, B, Ch, C);
+    PB_REQUIRE(C <= 1536 && Ch <= 1536, "se_fc_fwd: channel count too large for the shared-memory staging");
+    dim3 g1(ceil_div(Ch, 32), ceil_div(B, FC_BT));
+    fc_rows_kernel<PB_ACT_RELU><<<g1, 256, sizeof(float) * FC_BT * C, st>>>(mean, W1, b1, hidden, B, Ch, C);
     PB_CHECK_LAUNCH("se_fc_fwd(1)");
-    dim3 g2(ceil_div(C, 8), ceil_div(B, FC_BT));
-    fc_rows_kernel<PB_ACT_HSIGMOID><<<g2, 256, 0, st>>>(hidden, W2, b2, gate, B, C, Ch);
+    dim3 g2(ceil_div(C, 32), ceil_div(B, FC_BT));
+    fc_rows_kernel<PB_ACT_HSIGMOID><<<g2, 256, sizeof(float) * FC_BT * Ch, st>>>(hidden, W2, b2, gate, B, C, Ch);
     PB_CHECK_LAUNCH("se_fc_fwd(2)");
     return PB_OK;
 }
@@ -158,11 +174,13 @@ extern "C" int pb_se_fc_bwd(const float* dgate, const float* mean, const float* 
     PB_CHECK_LAUNCH("se_fc_bwd(hsig)");
     // da1[b][j] = relu'(hidden) * sum_c da2[b][c] * W2[c][j]   (W2 is [C][Ch] = "Wt" with K=C, N=Ch)
     dim3 g1(ceil_div(Ch, 32), ceil_div(B, FC_BT));
-    fc_cols_kernel<<<g1, 256, 0, st>>>(a2, W2, hidden, a1, B, Ch, C, 1.f);
+    PB_REQUIRE(C <= 1200 && Ch <= 1200, "se_fc_bwd: channel count too large for the shared-memory staging");
+    const size_t red_bytes = sizeof(float) * 8 * FC_BT * 33;
+    fc_cols_kernel<<<g1, 256, sizeof(float) * FC_BT * C + red_bytes, st>>>(a2, W2, hidden, a1, B, Ch, C, 1.f);
     PB_CHECK_LAUNCH("se_fc_bwd(da1)");
     // dmean[b][c] = inv_R * sum_j da1[b][j] * W1[j][c]         (W1 is [Ch][C] = "Wt" with K=Ch, N=C)
     dim3 g2(ceil_div(C, 32), ceil_div(B, FC_BT));
-    fc_cols_kernel<<<g2, 256, 0, st>>>(a1, W1, nullptr, dmean, B, C, Ch, inv_R);
+    fc_cols_kernel<<<g2, 256, sizeof(float) * FC_BT * Ch + red_bytes, st>>>(a1, W1, nullptr, dmean, B, C, Ch, inv_R);
     PB_CHECK_LAUNCH("se_fc_bwd(dmean)");
     long long n = 2LL * C * Ch + C + Ch;
     se_fc_bwd_param_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a2, a1, mean, hidden, dW1, db1, dW2, db2, B, C, Ch);
