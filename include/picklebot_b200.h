@@ -115,7 +115,11 @@ int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, int Bt, int 
  * BatchNorm3d/1d (+ activation + Dropout3d) -- mobilenet.py:80-82,90-92,142-143,180-181,247-248;
  * movinet.py:65,75-76,93,141-143,150-152.  Training mode uses batch statistics over the M rows.
  * ---------------------------------------------------------------------------------------------- */
-/* sums[0][c] = sum_m x, sums[1][c] = sum_m x^2 (fp64, overwritten). */
+/* Raw fp64 sums are accumulated into PB_STAT_REPLICAS interleaved copies (CTA i adds into copy
+ * i % PB_STAT_REPLICAS, which spreads the same-address atomics over more L2 lines); the finalize calls
+ * add the copies up.  Every `sums` argument below is a workspace of PB_STAT_REPLICAS*2*C doubles. */
+#define PB_STAT_REPLICAS 16
+/* sums[r][0][c] = partial sum_m x, sums[r][1][c] = partial sum_m x^2 (fp64, overwritten). */
 int pb_colstats(const void* x, int dtype, long long M, int C, double* sums, pb_stream_t stream);
 /* training: mean/var from sums, running stats updated (momentum, unbiased var), else running stats.
  * Writes scale = gamma*invstd, shift = beta - mean*scale, mean, invstd (all [C]). */

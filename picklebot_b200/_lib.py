@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libpicklebot_b200.so")
 
 PB_OK = 0
 PB_F32, PB_BF16, PB_U8, PB_F32_RBF16 = 0, 1, 2, 16
+STAT_REPLICAS = 16   # PB_STAT_REPLICAS in include/picklebot_b200.h
 ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_LRELU, ACT_HSIGMOID = 0, 1, 2, 3, 4
 
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float

@@ -30,8 +30,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double M, co
     if (c >= C) return;
     float mean, var;
     if (training) {
-        double mu = sums[c] / M;
-        double v = sums[C + c] / M - mu * mu;
+        double s0 = 0, s1 = 0;
+        for (int r = 0; r < PB_STAT_REPLICAS; ++r) { s0 += sums[r * 2 * C + c]; s1 += sums[r * 2 * C + C + c]; }
+        double mu = s0 / M;
+        double v = s1 / M - mu * mu;
         if (v < 0) v = 0;
         mean = (float)mu; var = (float)v;
         if (rmean) {
@@ -131,10 +133,11 @@ bn_bwd_reduce_kernel(const void* __restrict__ dout, const T* __restrict__ z, con
                      const float* __restrict__ shift, const float* __restrict__ mean,
                      const float* __restrict__ invstd, const float* __restrict__ mask, double* __restrict__ sums,
                      unsigned M, unsigned R, int C, float slope) {
-    extern __shared__ float sm_red[];   // [2][C]
+    __shared__ float sm_fold[16 * 256];
     const RowLayout L(C);
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm_red[i] = 0.f;
-    __syncthreads();
+    float s[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s[i] = 0.f;
     if (L.active) {
         float sc[8], sh[8], a[8], bb[8];
         load_vec8(scale + L.c0, sc);
@@ -143,9 +146,6 @@ bn_bwd_reduce_kernel(const void* __restrict__ dout, const T* __restrict__ z, con
         load_vec8(mean + L.c0, bb);
 #pragma unroll
         for (int i = 0; i < 8; ++i) bb[i] = -bb[i] * a[i];
-        float s0[8], s1[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
         const unsigned stride = gridDim.x * L.RPI;
         unsigned m = blockIdx.x * L.RPI + L.rr;
         for (; m + stride < M; m += 2 * stride) {           // two rows in flight
@@ -154,38 +154,38 @@ bn_bwd_reduce_kernel(const void* __restrict__ dout, const T* __restrict__ z, con
             bn_bwd_elem<T, ACT, BCAST>(dout, z, mask, m + stride, R, C, L.c0, sc, sh, a, bb, slope, d1, x1);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                s0[i] += d0[i] + d1[i];
-                s1[i] = fmaf(d0[i], x0[i], fmaf(d1[i], x1[i], s1[i]));
+                s[i] += d0[i] + d1[i];
+                s[8 + i] = fmaf(d0[i], x0[i], fmaf(d1[i], x1[i], s[8 + i]));
             }
         }
         if (m < M) {
             float d0[8], x0[8];
             bn_bwd_elem<T, ACT, BCAST>(dout, z, mask, m, R, C, L.c0, sc, sh, a, bb, slope, d0, x0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s0[i] += d0[i]; s1[i] = fmaf(d0[i], x0[i], s1[i]); }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            atomicAdd(&sm_red[L.c0 + i], s0[i]);
-            atomicAdd(&sm_red[C + L.c0 + i], s1[i]);
+            for (int i = 0; i < 8; ++i) { s[i] += d0[i]; s[8 + i] = fmaf(d0[i], x0[i], s[8 + i]); }
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)sm_red[i]);
+    cta_fold_rows<16>(s, L.G, L.RPI, L.rr, sm_fold);
+    if (L.rr == 0) {
+        double* dst = sums + (size_t)(blockIdx.x % PB_STAT_REPLICAS) * 2 * C;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            atomicAdd(&dst[L.c0 + i], (double)s[i]);
+            atomicAdd(&dst[C + L.c0 + i], (double)s[8 + i]);
+        }
+    }
 }
 
 // batch statistics: sums[0][c] = sum z, sums[1][c] = sum z^2 (four rows in flight per thread)
 template <typename T>
 __global__ void __launch_bounds__(256)
 colstats_kernel(const T* __restrict__ z, double* __restrict__ sums, unsigned M, int C) {
-    extern __shared__ float sm_red[];   // [2][C]
+    __shared__ float sm_fold[16 * 256];
     const RowLayout L(C);
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm_red[i] = 0.f;
-    __syncthreads();
-    if (L.active) {
-        float s0[8], s1[8];
+    float s[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+    for (int i = 0; i < 16; ++i) s[i] = 0.f;
+    if (L.active) {
         const unsigned stride = gridDim.x * L.RPI;
         unsigned m = blockIdx.x * L.RPI + L.rr;
         for (; m + 3 * stride < M; m += 4 * stride) {
@@ -195,21 +195,23 @@ colstats_kernel(const T* __restrict__ z, double* __restrict__ sums, unsigned M, 
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { s0[i] += v[u].v[i]; s1[i] = fmaf(v[u].v[i], v[u].v[i], s1[i]); }
+                for (int i = 0; i < 8; ++i) { s[i] += v[u].v[i]; s[8 + i] = fmaf(v[u].v[i], v[u].v[i], s[8 + i]); }
         }
         for (; m < M; m += stride) {
             const F8 v = load8(z + (size_t)m * C + L.c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s0[i] += v.v[i]; s1[i] = fmaf(v.v[i], v.v[i], s1[i]); }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            atomicAdd(&sm_red[L.c0 + i], s0[i]);
-            atomicAdd(&sm_red[C + L.c0 + i], s1[i]);
+            for (int i = 0; i < 8; ++i) { s[i] += v.v[i]; s[8 + i] = fmaf(v.v[i], v.v[i], s[8 + i]); }
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], (double)sm_red[i]);
+    cta_fold_rows<16>(s, L.G, L.RPI, L.rr, sm_fold);
+    if (L.rr == 0) {
+        double* dst = sums + (size_t)(blockIdx.x % PB_STAT_REPLICAS) * 2 * C;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            atomicAdd(&dst[L.c0 + i], (double)s[i]);
+            atomicAdd(&dst[C + L.c0 + i], (double)s[8 + i]);
+        }
+    }
 }
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double M, int training,
@@ -217,7 +219,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double M
                                        float* __restrict__ coef, int C) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    double s0 = sums[c], s1 = sums[C + c];
+    double s0 = 0, s1 = 0;
+    for (int r = 0; r < PB_STAT_REPLICAS; ++r) { s0 += sums[r * 2 * C + c]; s1 += sums[r * 2 * C + C + c]; }
     if (dbeta) dbeta[c] = (float)s0;
     if (dgamma) dgamma[c] = (float)s1;
     coef[c] = training ? (float)(s0 / M) : 0.f;
@@ -280,11 +283,11 @@ using namespace pb;
 extern "C" int pb_colstats(const void* x, int dtype, long long M, int C, double* sums, pb_stream_t stream) {
     PB_REQUIRE(x && sums && M > 0 && C > 0 && C % 8 == 0 && C <= 2048, "colstats: bad args (M=%lld C=%d)", M, C);
     cudaStream_t st = (cudaStream_t)stream;
-    PB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    PB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * PB_STAT_REPLICAS * 2 * C, st));
     PB_REQUIRE(M < (1LL << 31), "colstats: too many rows");
     const int grid = row_grid(M, C);
     PB_DISPATCH_DTYPE(dtype, {
-        colstats_kernel<T><<<grid, 256, sizeof(float) * 2 * C, st>>>((const T*)x, sums, (unsigned)M, C);
+        colstats_kernel<T><<<grid, 256, 0, st>>>((const T*)x, sums, (unsigned)M, C);
     });
     PB_CHECK_LAUNCH("colstats");
     return PB_OK;
@@ -325,9 +328,9 @@ extern "C" int pb_bn_act_bwd_reduce(const void* dout, int dout_bcast, const void
     const long long M = (long long)B * R;
     PB_REQUIRE(M < (1LL << 31) && R < (1LL << 31), "bn_act_bwd_reduce: too many rows");
     cudaStream_t st = (cudaStream_t)stream;
-    PB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    PB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * PB_STAT_REPLICAS * 2 * C, st));
     const int grid = row_grid(M, C);
-    const size_t smem = sizeof(float) * 2 * C;
+    const size_t smem = 0;
     PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
         if (dout_bcast)
             bn_bwd_reduce_kernel<T, ACT, true><<<grid, 256, smem, st>>>(dout, (const T*)z, scale, shift, mean, invstd,

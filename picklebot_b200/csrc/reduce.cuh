@@ -9,24 +9,43 @@ namespace pb {
 
 constexpr int COLRED_UNROLL = 2;
 
+// Fold the per-thread partials of one CTA over the row-slot index rr (threads tid and tid+h*G own the same
+// channels): a halving tree through shared memory (channel-major, so every access is conflict-free).  On
+// return the rr==0 threads hold the CTA totals.  Replaces per-thread shared-memory atomics, which serialise
+// RPI-way on the same address when C is small.
+template <int NACC>
+__device__ __forceinline__ void cta_fold_rows(float (&acc)[NACC], int G, int RPI, int rr, float* sm /*[NACC][256]*/) {
+    const int tid = threadIdx.x;
+    for (int n = RPI; n > 1;) {
+        const int half = (n + 1) >> 1;
+        if (rr >= half && rr < n) {
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) sm[j * 256 + tid] = acc[j];
+        }
+        __syncthreads();
+        if (rr + half < n) {
+#pragma unroll
+            for (int j = 0; j < NACC; ++j) acc[j] += sm[j * 256 + tid + half * G];
+        }
+        __syncthreads();
+        n = half;
+    }
+}
+
 // F: struct with  __device__ void operator()(int batch, long long row_in_batch, int c0, float (&out)[NV][8]) const
 template <typename F, int NV, typename OUT>
 __global__ void __launch_bounds__(256)
 colreduce_kernel(F f, long long R, int C, OUT* __restrict__ out, int nbatch, float out_scale) {
-    extern __shared__ float sm_red[];   // [NV][C]
+    __shared__ float sm_fold[NV * 8 * 256];
     const int G = C >> 3;
     const int RPI = blockDim.x / G;
     const int g = threadIdx.x % G, rr = threadIdx.x / G;
     const int b = blockIdx.y;
-    for (int i = threadIdx.x; i < NV * C; i += blockDim.x) sm_red[i] = 0.f;
-    __syncthreads();
+    float acc[NV * 8];
+#pragma unroll
+    for (int i = 0; i < NV * 8; ++i) acc[i] = 0.f;
+    const int c0 = g << 3;
     if (rr < RPI) {
-        float acc[NV][8];
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
-        const int c0 = g << 3;
         const long long stride = (long long)gridDim.x * RPI;
         long long r = (long long)blockIdx.x * RPI + rr;
         for (; r + (COLRED_UNROLL - 1) * stride < R; r += COLRED_UNROLL * stride) {
@@ -38,7 +57,7 @@ colreduce_kernel(F f, long long R, int C, OUT* __restrict__ out, int nbatch, flo
 #pragma unroll
                 for (int v = 0; v < NV; ++v)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[v][i] += t[u][v][i];
+                    for (int i = 0; i < 8; ++i) acc[v * 8 + i] += t[u][v][i];
         }
         for (; r < R; r += stride) {
             float t[NV][8];
@@ -46,17 +65,16 @@ colreduce_kernel(F f, long long R, int C, OUT* __restrict__ out, int nbatch, flo
 #pragma unroll
             for (int v = 0; v < NV; ++v)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[v][i] += t[v][i];
+                for (int i = 0; i < 8; ++i) acc[v * 8 + i] += t[v][i];
         }
+    }
+    cta_fold_rows<NV * 8>(acc, G, RPI, rr, sm_fold);
+    if (rr == 0) {
 #pragma unroll
         for (int v = 0; v < NV; ++v)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(&sm_red[v * C + c0 + i], acc[v][i]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < NV * C; i += blockDim.x) {
-        int v = i / C, c = i % C;
-        atomicAdd(&out[((long long)v * nbatch + b) * C + c], (OUT)(sm_red[i] * out_scale));
+            for (int i = 0; i < 8; ++i)
+                atomicAdd(&out[((long long)v * nbatch + b) * C + c0 + i], (OUT)(acc[v * 8 + i] * out_scale));
     }
 }
 

@@ -57,7 +57,7 @@ extern "C" int pb_pool_fwd(const void* x, int dtype, int B, long long R, int C, 
     dim3 grid = colreduce_grid(R, C, B);
     PB_DISPATCH_DTYPE(dtype, {
         PoolF<T> f{(const T*)x, R, C};
-        colreduce_kernel<PoolF<T>, 1, float><<<grid, 256, sizeof(float) * C, st>>>(f, R, C, mean, B, 1.f / (float)R);
+        colreduce_kernel<PoolF<T>, 1, float><<<grid, 256, 0, st>>>(f, R, C, mean, B, 1.f / (float)R);
     });
     PB_CHECK_LAUNCH("pool_fwd");
     return PB_OK;
@@ -71,7 +71,7 @@ extern "C" int pb_rowdot(const void* g, const void* y, int dtype, int B, long lo
     dim3 grid = colreduce_grid(R, C, B);
     PB_DISPATCH_DTYPE(dtype, {
         DotF<T> f{(const T*)g, (const T*)y, R, C};
-        colreduce_kernel<DotF<T>, 1, float><<<grid, 256, sizeof(float) * C, st>>>(f, R, C, out, B, 1.f);
+        colreduce_kernel<DotF<T>, 1, float><<<grid, 256, 0, st>>>(f, R, C, out, B, 1.f);
     });
     PB_CHECK_LAUNCH("rowdot");
     return PB_OK;

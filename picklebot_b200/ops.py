@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_HSIGMOID, ACT_HSWISH, ACT_LRELU, ACT_NONE, ACT_RELU, PB_BF16, PB_F32, PB_F32_RBF16,
-                   PB_U8)
+                   PB_U8, STAT_REPLICAS)
 
 
 def call(name, *args, nbytes=0, tag=""):
@@ -198,7 +198,7 @@ def wgrad_simt(A: torch.Tensor, dC: torch.Tensor, K: int, N: int, ascale=None, B
 def colstats(x: torch.Tensor, C: int) -> torch.Tensor:
     _chk(x, "colstats.x")
     M = x.numel() // C
-    sums = torch.empty((2, C), dtype=torch.float64, device=x.device)
+    sums = torch.empty((STAT_REPLICAS, 2, C), dtype=torch.float64, device=x.device)
     call("pb_colstats", x.data_ptr(), _dt(x), M, C, sums.data_ptr(), _st(), nbytes=x.numel() * x.element_size())
     return sums
 
@@ -227,7 +227,7 @@ def bn_act_bwd(dout: torch.Tensor, dout_bcast: bool, z: torch.Tensor, scale, shi
     R = z.numel() // (B * C)
     M = B * R
     dev = z.device
-    sums = torch.empty((2, C), dtype=torch.float64, device=dev)
+    sums = torch.empty((STAT_REPLICAS, 2, C), dtype=torch.float64, device=dev)
     call("pb_bn_act_bwd_reduce", dout.data_ptr(), int(dout_bcast), z.data_ptr(), scale.data_ptr(), shift.data_ptr(),
          mean.data_ptr(), invstd.data_ptr(), _p(mask), sums.data_ptr(), _dt(z), B, R, C, act, slope, _st(),
          nbytes=(z.numel() + (0 if dout_bcast else dout.numel())) * z.element_size())
