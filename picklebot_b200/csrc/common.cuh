@@ -52,6 +52,32 @@ void count_launch(int n = 1);
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched through launch_pdl may be scheduled while the previous
+// kernel of the stream is still draining; everything it does before pdl_wait() (barrier init, TMEM
+// allocation, descriptor prefetch, per-channel constants) overlaps that tail.  pdl_wait() returns once the
+// previous kernel has completed and its writes are visible, so it must precede the first global-memory
+// access that can alias another kernel's output -- and every thread of every such kernel must reach it,
+// because the next kernel in the chain relies on this one not finishing before its predecessor.
+// pdl_trigger() (first statement) lets the next kernel's CTAs be scheduled as soon as all of ours started.
+// PB_PDL=0 in the environment launches everything fully serialised (the instructions become no-ops).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // 8-channel vectors: one 16-byte access for bf16, two for fp32
 // ---------------------------------------------------------------------------------------------
 struct F8 { float v[8]; };

@@ -66,6 +66,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
+    pdl_trigger();
 
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);      // 1024-byte aligned (SWIZZLE_128B)
@@ -90,6 +91,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();      // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
@@ -274,7 +276,7 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = (int)std::min<long long>(p.total_tiles, sms);
-    gemm_tc_kernel<<<grid, 384, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
+    PB_CUDA(launch_pdl(gemm_tc_kernel, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
     PB_CHECK_LAUNCH("gemm_tc_kernel");
     return PB_OK;
 }

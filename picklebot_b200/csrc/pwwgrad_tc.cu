@@ -19,45 +19,98 @@
 namespace pb {
 namespace tc {
 
-// rows (reduction) per pipeline stage: 64, or 128 for skinny layers (few boxes per stage) where the fixed
-// per-stage cost would otherwise dominate; one TMA box = rows x 64 bf16 elements (rows x 128 bytes)
-constexpr int WG_STAGES_MAX = 4;
+// Operand boxes: one TMA box = rows x ew channels, ew in {16, 32, 64} (swizzle 32/64/128 bytes) picked per
+// operand so that narrow layers (16..112 channels) do not fill shared memory with out-of-bounds zeros: the
+// bytes in flight per SM are what bounds a streaming reduction, so every staged byte should be a useful one.
+// rows (reduction) per pipeline stage: 64, 128 or 256 -- the fewer columns a stage holds the more rows.
+constexpr int WG_STAGES_MAX = 8;
 
 struct WgradPlan {
+    int fold;        // F consecutive rows are viewed as one row of F*C channels (see make_plan)
     int NT;          // 128-row output tiles along n
     int KW;          // k-slice width per item (multiple of 16, <= 256)
     int k_groups;    // slices along k
     int per_group;   // n-tiles per item (per_group * KW <= 512)
     int n_groups;
-    int kw_boxes;    // ceil(KW / 64)
+    int ew_d, ew_a;  // box width (channels) of the dC / A operand
+    int nb_d;        // dC boxes per 128-wide n-tile
+    int kw_boxes;    // A boxes per item: ceil(KW / ew_a)
     int chunks;      // row chunks per batch entry
     long long chunk_rows;   // multiple of rows
-    int rows;               // reduction rows per stage (64 or 128)
-    int box_bytes;          // rows * 128
+    int rows;               // reduction rows per stage
+    int box_bytes_d, box_bytes_a;
     int stages;
     int stage_bytes;
+    int slack_bytes;        // the 128-wide MMA operand of a narrow dC tile reads past the boxes that were loaded
     long long items;        // groups * chunks * Bt
 };
 
+// box width for an operand of W channels: least padding, fewer boxes on ties
+static int pick_box_width(int W) {
+    if (W > 128) return 64;
+    int best = 64, best_cost = 1 << 30;
+    for (int ew : {64, 32, 16}) {
+        const int boxes = ceil_div(W, ew);
+        const int cost = boxes * ew + 4 * boxes;
+        if (cost < best_cost) { best_cost = cost; best = ew; }
+    }
+    return best;
+}
+
+// Row folding.  The TMA unit spends about as long on a 32-byte box row as on a 128-byte one, so a 16- or
+// 32-channel activation matrix cannot be streamed at HBM speed row by row.  Since X[M][C] is contiguous it is
+// also X'[M/F][F*C]; the product of the folded operands, P'[(i,n)][(j,k)] = sum_r' dC[F r'+i][n] A[F r'+j][k],
+// holds the wanted sum in its F diagonal blocks (i == j) -- the off-diagonal MMA work is free, the kernel
+// is nowhere near tensor-bound -- and the epilogue writes block i as one more partial slice.
+static int pick_fold(long long R, int K, int N) {
+    if (std::min(K, N) > 32) return 1;
+    for (int F : {4, 2})
+        if (R % F == 0 && K * F <= 128 && N * F <= 128) return F;
+    return 1;
+}
+
 static WgradPlan make_plan(int Bt, long long R, int K, int N) {
     WgradPlan p;
+    p.fold = pick_fold(R, K, N);
+    R /= p.fold; K *= p.fold; N *= p.fold;      // from here on: the folded problem
     p.NT = ceil_div(N, 128);
     int kg = ceil_div(K, 256);
     p.KW = (ceil_div(K, kg) + 15) / 16 * 16;
     p.k_groups = ceil_div(K, p.KW);
-    p.kw_boxes = ceil_div(p.KW, 64);
+    p.ew_d = pick_box_width(N);
+    p.ew_a = pick_box_width(p.k_groups > 1 ? 256 : K);
+    p.nb_d = p.NT > 1 ? 128 / p.ew_d : ceil_div(N, p.ew_d);
+    p.kw_boxes = ceil_div(p.KW, p.ew_a);
+    const int tile_cols = p.nb_d * p.ew_d, a_cols = p.kw_boxes * p.ew_a;
     p.per_group = std::max(1, std::min(p.NT, 512 / p.KW));
-    p.per_group = std::max(1, std::min(p.per_group, (13 - p.kw_boxes) / 2));   // two stages must fit in 216 KB
+    // two 64-row stages must fit in 216 KB
+    p.per_group = std::max(1, std::min(p.per_group, (216 * 1024 / (2 * 64 * 2) - a_cols) / tile_cols));
     p.n_groups = ceil_div(p.NT, p.per_group);
-    p.rows = (p.per_group * 2 + p.kw_boxes) <= 4 ? 128 : 64;
-    p.box_bytes = p.rows * 128;
-    p.stage_bytes = (p.per_group * 2 + p.kw_boxes) * p.box_bytes;
-    p.stages = std::max(2, std::min(WG_STAGES_MAX, (216 * 1024) / p.stage_bytes));
-    // aim at ~4 items per SM so the persistent CTAs stay balanced, but keep >= 1024 rows per item
-    long long groups = (long long)p.k_groups * p.n_groups;
-    long long want = std::max<long long>(1, (148LL * 4 + Bt * groups - 1) / (Bt * groups));
-    long long max_chunks = std::max<long long>(1, R / 1024);
-    p.chunks = (int)std::min(want, max_chunks);
+    const int cols = p.per_group * tile_cols + a_cols;
+    p.rows = cols <= 64 ? 256 : cols <= 256 ? 128 : 64;
+    p.box_bytes_d = p.rows * p.ew_d * 2;
+    p.box_bytes_a = p.rows * p.ew_a * 2;
+    p.stage_bytes = cols * p.rows * 2;
+    p.slack_bytes = (128 / p.ew_d - p.nb_d) * p.box_bytes_d;
+    p.stages = std::max(2, std::min(WG_STAGES_MAX, (216 * 1024 - p.slack_bytes) / p.stage_bytes));
+    // Row chunks: items are equal-sized and statically assigned, so what matters is that their count fills
+    // whole waves of 148 CTAs; fewer, longer items also mean fewer fp32 partials to write and re-read.
+    // Keep >= 1024 rows per item.
+    const long long groups = (long long)p.k_groups * p.n_groups;
+    const long long unit = Bt * groups;
+    const long long max_chunks = std::max<long long>(1, R / 1024);
+    long long best = std::min(max_chunks, std::max<long long>(1, 148 / unit));
+    if (unit * max_chunks > 148) {
+        double best_eff = 0;
+        for (int w = 1; w <= 4; ++w) {
+            const long long c = std::min(max_chunks, (148LL * w) / unit);
+            if (c < 1) continue;
+            const long long it = unit * c;
+            const double eff = (double)it / (148.0 * (double)((it + 147) / 148));
+            if (eff > best_eff + 0.03) { best_eff = eff; best = c; }
+        }
+    }
+    p.chunks = (int)best;
     p.chunk_rows = ((R + p.chunks - 1) / p.chunks + p.rows - 1) / p.rows * p.rows;
     p.chunks = (int)((R + p.chunk_rows - 1) / p.chunk_rows);
     p.items = groups * p.chunks * Bt;
@@ -65,8 +118,8 @@ static WgradPlan make_plan(int Bt, long long R, int K, int N) {
 }
 
 struct WgradParams {
-    int Bt, K, N;
-    long long R;
+    int Bt, K, N;       // K, N: the real (unfolded) channel counts
+    long long R;        // rows per batch entry of the folded problem
     WgradPlan plan;
     float* partial;     // [Bt][chunks][N][K]
 };
@@ -88,11 +141,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[WG_STAGES_MAX], empty_bar[WG_STAGES_MAX], done_bar, tfree_bar;
     __shared__ uint32_t tmem_base_s;
+    pdl_trigger();
     const WgradPlan& pl = p.plan;
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* tiles = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int d_bytes = pl.per_group * 2 * pl.box_bytes;   // dC part of a stage
+    const int tile_bytes_d = pl.nb_d * pl.box_bytes_d;
+    const int d_bytes = pl.per_group * tile_bytes_d;       // dC part of a stage
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmD);
@@ -107,6 +162,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -119,16 +175,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
                 const long long r_begin = (long long)w.chunk * pl.chunk_rows;
                 const long long r_end = min(p.R, r_begin + pl.chunk_rows);
                 const int iters = (int)((r_end - r_begin + pl.rows - 1) / pl.rows);
-                const uint32_t tx = (uint32_t)((ntiles * 2 + pl.kw_boxes) * pl.box_bytes);
+                const uint32_t tx = (uint32_t)(ntiles * tile_bytes_d + pl.kw_boxes * pl.box_bytes_a);
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_expect_tx(&full_bar[s], tx);
                     uint8_t* st = tiles + (size_t)s * pl.stage_bytes;
                     const int r = (int)(r_begin + (long long)it * pl.rows);
-                    for (int j = 0; j < ntiles * 2; ++j)
-                        tma_load_3d(st + j * pl.box_bytes, &tmD, &full_bar[s], (nt0 * 2 + j) * 64, r, w.b);
+                    for (int j = 0; j < ntiles * pl.nb_d; ++j)
+                        tma_load_3d(st + j * pl.box_bytes_d, &tmD, &full_bar[s], nt0 * 128 + j * pl.ew_d, r, w.b);
                     for (int j = 0; j < pl.kw_boxes; ++j)
-                        tma_load_3d(st + d_bytes + j * pl.box_bytes, &tmA, &full_bar[s], k0 + j * 64, r, w.b);
+                        tma_load_3d(st + d_bytes + j * pl.box_bytes_a, &tmA, &full_bar[s], k0 + j * pl.ew_a, r, w.b);
                     if (++s == pl.stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -136,6 +192,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(128, pl.KW, 1, 1);
+            // MN-major canonical layouts: an atom is 8 rows x ew channels (16*ew bytes); SBO = atom stride along
+            // the rows, LBO = stride between ew-wide channel groups (= one box); one MMA eats 16 rows = 2 atoms
+            const uint32_t atom_d = 16u * pl.ew_d, atom_a = 16u * pl.ew_a;
+            const uint32_t type_d = pl.ew_d == 64 ? 2u : pl.ew_d == 32 ? 4u : 6u;
+            const uint32_t type_a = pl.ew_a == 64 ? 2u : pl.ew_a == 32 ? 4u : 6u;
             int s = 0; uint32_t ph = 0;
             uint32_t n_item = 0;
             for (long long item = blockIdx.x; item < pl.items; item += gridDim.x, ++n_item) {
@@ -154,9 +215,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
                     tc_fence_after();
                     const uint32_t sb = smem_u32(tiles + (size_t)s * pl.stage_bytes);
                     for (int j = 0; j < ntiles; ++j) {
-                        for (int ks = 0; ks < pl.rows / 16; ++ks) {     // 16 rows = 2 swizzle atoms = 2 KB
-                            const uint64_t adesc = make_desc(sb + j * 2 * pl.box_bytes + ks * 2048, pl.box_bytes, 1024);
-                            const uint64_t bdesc = make_desc(sb + d_bytes + ks * 2048, pl.box_bytes, 1024);
+                        for (int ks = 0; ks < pl.rows / 16; ++ks) {
+                            const uint64_t adesc = make_desc(sb + j * tile_bytes_d + ks * 2 * atom_d, pl.box_bytes_d,
+                                                             atom_d, type_d);
+                            const uint64_t bdesc = make_desc(sb + d_bytes + ks * 2 * atom_a, pl.box_bytes_a, atom_a,
+                                                             type_a);
                             umma_bf16(tmem_base + (uint32_t)(j * pl.KW), adesc, bdesc, idesc, (it | ks) != 0);
                         }
                     }
@@ -176,24 +239,45 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
             const int k0 = w.kg * pl.KW;
             mbar_wait(&done_bar, n_item & 1);
             tc_fence_after();
-            float* out = p.partial + ((long long)w.b * pl.chunks + w.chunk) * p.N * p.K;
-            for (int j = 0; j < ntiles; ++j) {
-                const int n = (nt0 + j) * 128 + q * 32 + lane;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * pl.KW);
+            const long long slice = (long long)w.b * pl.chunks + w.chunk;
+            if (pl.fold == 1) {
+                float* out = p.partial + slice * p.N * p.K;
+                for (int j = 0; j < ntiles; ++j) {
+                    const int n = (nt0 + j) * 128 + q * 32 + lane;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * pl.KW);
+                    for (int c0 = 0; c0 < pl.KW; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(taddr + (uint32_t)c0, r);
+                        tmem_ld_wait();
+                        const int k = k0 + c0;
+                        if (n < p.N && k < p.K) {
+                            float* dst = out + (long long)n * p.K + k;
+                            const int nv = min(16, p.K - k);            // 8 or 16
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(r[0], r[1], r[2], r[3]);
+                            *reinterpret_cast<uint4*>(dst + 4) = make_uint4(r[4], r[5], r[6], r[7]);
+                            if (nv > 8) {
+                                *reinterpret_cast<uint4*>(dst + 8) = make_uint4(r[8], r[9], r[10], r[11]);
+                                *reinterpret_cast<uint4*>(dst + 12) = make_uint4(r[12], r[13], r[14], r[15]);
+                            }
+                        }
+                    }
+                }
+            } else {
+                // folded: one tile; TMEM lane (i, n) keeps the columns of diagonal block i -> partial slice i
+                const int np = q * 32 + lane;
+                const int i = np / p.N, n = np - i * p.N;
+                const bool live = i < pl.fold;
+                float* dst = p.partial + ((slice * pl.fold + i) * p.N + n) * p.K;
+                const int lo = i * p.K, hi = lo + p.K;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
                 for (int c0 = 0; c0 < pl.KW; c0 += 16) {
                     uint32_t r[16];
                     tmem_ld16(taddr + (uint32_t)c0, r);
                     tmem_ld_wait();
-                    const int k = k0 + c0;
-                    if (n < p.N && k < p.K) {
-                        float* dst = out + (long long)n * p.K + k;
-                        const int nv = min(16, p.K - k);            // 8 or 16
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(r[0], r[1], r[2], r[3]);
-                        *reinterpret_cast<uint4*>(dst + 4) = make_uint4(r[4], r[5], r[6], r[7]);
-                        if (nv > 8) {
-                            *reinterpret_cast<uint4*>(dst + 8) = make_uint4(r[8], r[9], r[10], r[11]);
-                            *reinterpret_cast<uint4*>(dst + 12) = make_uint4(r[12], r[13], r[14], r[15]);
-                        }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int col = c0 + e;
+                        if (live && col >= lo && col < hi) dst[col - lo] = __uint_as_float(r[e]);
                     }
                 }
             }
@@ -216,6 +300,8 @@ __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ gate,
                     float* __restrict__ dW, int Bt, int chunks, int N, int K) {
     __shared__ float red[8][33];
+    pdl_trigger();
+    pdl_wait();
     const int ol = threadIdx.x & 31, ps = threadIdx.x >> 5;
     const long long NK = (long long)N * K;
     const long long idx = (long long)blockIdx.x * 32 + ol;
@@ -241,6 +327,8 @@ wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__
 // dgate[b][k] = sum_n W[n][k] * P_b[n][k],  P_b = sum_c partial[b][c]
 __global__ void wgrad_dgate_kernel(const float* __restrict__ partial, const float* __restrict__ W,
                                    float* __restrict__ dgate, int Bt, int chunks, int N, int K) {
+    pdl_trigger();
+    pdl_wait();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (k >= K) return;
@@ -262,7 +350,7 @@ using namespace pb::tc;
 extern "C" long long pb_pw_wgrad_tc_workspace_bytes(int Bt, long long R, int K, int N) {
     if (Bt <= 0 || R <= 0 || K <= 0 || N <= 0) return 0;
     WgradPlan pl = make_plan(Bt, R, K, N);
-    return (long long)Bt * pl.chunks * N * K * (long long)sizeof(float);
+    return (long long)Bt * pl.chunks * pl.fold * N * K * (long long)sizeof(float);
 }
 
 extern "C" int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, const float* Wf32, void* workspace,
@@ -272,22 +360,24 @@ extern "C" int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, 
     PB_REQUIRE(K % 8 == 0 && N % 8 == 0, "pw_wgrad_tc: K=%d and N=%d must be multiples of 8", K, N);
     PB_REQUIRE(!dgate || (Wf32 != nullptr), "pw_wgrad_tc: dgate needs the fp32 weights");
     WgradParams p;
-    p.Bt = Bt; p.K = K; p.N = N; p.R = R;
+    p.Bt = Bt; p.K = K; p.N = N;
     p.plan = make_plan(Bt, R, K, N);
+    p.R = R / p.plan.fold;
     p.partial = (float*)workspace;
     const WgradPlan& pl = p.plan;
+    const uint64_t F = (uint64_t)pl.fold;
     CUtensorMap tmD, tmA;
     {
-        uint64_t dims[3] = {(uint64_t)N, (uint64_t)R, (uint64_t)Bt};
-        uint64_t str[3] = {2, (uint64_t)N * 2, (uint64_t)R * N * 2};
-        uint32_t box[3] = {64, (uint32_t)pl.rows, 1};
-        if (int e = make_tmap_bf16(&tmD, dC, 3, dims, str, box)) return e;
+        uint64_t dims[3] = {(uint64_t)N * F, (uint64_t)R / F, (uint64_t)Bt};
+        uint64_t str[3] = {2, (uint64_t)N * F * 2, (uint64_t)R * N * 2};
+        uint32_t box[3] = {(uint32_t)pl.ew_d, (uint32_t)pl.rows, 1};
+        if (int e = make_tmap_bf16(&tmD, dC, 3, dims, str, box, pl.ew_d * 2)) return e;
     }
     {
-        uint64_t dims[3] = {(uint64_t)K, (uint64_t)R, (uint64_t)Bt};
-        uint64_t str[3] = {2, (uint64_t)K * 2, (uint64_t)R * K * 2};
-        uint32_t box[3] = {64, (uint32_t)pl.rows, 1};
-        if (int e = make_tmap_bf16(&tmA, A, 3, dims, str, box)) return e;
+        uint64_t dims[3] = {(uint64_t)K * F, (uint64_t)R / F, (uint64_t)Bt};
+        uint64_t str[3] = {2, (uint64_t)K * F * 2, (uint64_t)R * K * 2};
+        uint32_t box[3] = {(uint32_t)pl.ew_a, (uint32_t)pl.rows, 1};
+        if (int e = make_tmap_bf16(&tmA, A, 3, dims, str, box, pl.ew_a * 2)) return e;
     }
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
@@ -300,15 +390,17 @@ extern "C" int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)std::min<long long>(pl.items, sms);
-    const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024;
-    wgrad_tc_kernel<<<grid, 256, smem, st>>>(tmD, tmA, p);
+    const size_t smem = (size_t)pl.stages * pl.stage_bytes + pl.slack_bytes + 1024;
+    PB_CUDA(launch_pdl(wgrad_tc_kernel, dim3(grid), dim3(256), smem, st, tmD, tmA, p));
     PB_CHECK_LAUNCH("wgrad_tc_kernel");
     const long long NK = (long long)N * K;
-    wgrad_reduce_kernel<<<ceil_div(NK, 32), 256, 0, st>>>(p.partial, gate, dW, Bt, pl.chunks, N, K);
+    PB_CUDA(launch_pdl(wgrad_reduce_kernel, dim3(ceil_div(NK, 32)), dim3(256), 0, st, (const float*)p.partial, gate, dW, Bt,
+                       pl.chunks * pl.fold, N, K));
     PB_CHECK_LAUNCH("wgrad_reduce_kernel");
     if (dgate) {
         dim3 g2(ceil_div(K, 128), Bt);
-        wgrad_dgate_kernel<<<g2, 128, 0, st>>>(p.partial, Wf32, dgate, Bt, pl.chunks, N, K);
+        PB_CUDA(launch_pdl(wgrad_dgate_kernel, g2, dim3(128), 0, st, (const float*)p.partial, Wf32, dgate, Bt,
+                           pl.chunks * pl.fold, N, K));
         PB_CHECK_LAUNCH("wgrad_dgate_kernel");
     }
     return PB_OK;

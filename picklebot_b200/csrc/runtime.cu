@@ -1,4 +1,5 @@
 // Error strings, launch counter and device check for the C ABI (include/picklebot_b200.h).
+#include <cstdlib>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -23,6 +24,10 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("PB_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 }  // namespace pb
 

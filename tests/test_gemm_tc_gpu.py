@@ -62,7 +62,10 @@ def test_gemm_tc_matches_simt_bitwise_scale():
 # (Bt, R, K, N): K = input channels of the layer, N = its output channels
 WGRAD_CASES = [(1, 4096, 16, 16), (1, 100000, 16, 64), (1, 7000, 24, 72), (1, 50000, 72, 24), (2, 931, 960, 160),
                (1, 59584, 160, 960), (3, 777, 672, 112), (1, 3000, 112, 672), (4, 100, 72, 40), (1, 12544, 80, 184),
-               (64, 735, 960, 160), (1, 65, 8, 8), (2, 5000, 144, 576), (1, 20000, 576, 144), (1, 6000, 40, 240)]
+               (64, 735, 960, 160), (1, 65, 8, 8), (2, 5000, 144, 576), (1, 20000, 576, 144), (1, 6000, 40, 240),
+               (1, 30000, 40, 120), (1, 9000, 120, 40), (1, 5000, 88, 24), (1, 3000, 96, 40), (2, 2000, 48, 144),
+               (1, 2500, 32, 32), (1, 2500, 64, 64), (1, 2500, 128, 128), (1, 2500, 104, 56),
+               (3, 1000, 16, 24), (2, 998, 24, 32), (5, 444, 32, 8)]   # row-folded plans
 
 
 @pytest.mark.parametrize("case", WGRAD_CASES)
