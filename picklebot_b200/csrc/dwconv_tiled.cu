@@ -141,7 +141,9 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
     const int tid = threadIdx.x;
     const int c_base = blockIdx.y * p.Cb;
     const int cb_bytes = p.Cb * 2;
+    pdl_trigger();
     pipeline_init(cx, p);
+    pdl_wait();                 // barrier setup above overlaps the previous kernel's tail
     const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid >= DWT_CONSUMERS) {
@@ -272,7 +274,9 @@ dw_dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmD, const float* __r
     const int tid = threadIdx.x;
     const int c_base = blockIdx.y * p.Cb;
     const int cb_bytes = p.Cb * 2;
+    pdl_trigger();
     pipeline_init(cx, p);
+    pdl_wait();                 // barrier setup above overlaps the previous kernel's tail
     const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid >= DWT_CONSUMERS) {
@@ -387,7 +391,9 @@ dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int c_base = blockIdx.y * p.Cb;
     const int cb_bytes = p.Cb * 2;
     const int x_bytes = (p.box_bytes + 127) / 128 * 128;       // dy tile follows the x tile in a stage
+    pdl_trigger();
     pipeline_init(cx, p);
+    pdl_wait();                 // barrier setup above overlaps the previous kernel's tail
     const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid == DWT_CONSUMERS) {
@@ -589,7 +595,8 @@ static bool launch_fwd(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16*
     if (make_map5(&tm, x, d.C, d.W, d.H, d.T, d.B, p.Cb, p.Wi, p.Hi) != PB_OK) return false;
     static std::once_flag once;
     set_smem_once(dw_fwd_tma_kernel<K, S, WS>, once);
-    dw_fwd_tma_kernel<K, S, WS><<<persistent_grid(p), DWT_THREADS, (size_t)p.stages * p.stage_bytes + 128, st>>>(tm, w_tc, y, p);
+    (void)launch_pdl(dw_fwd_tma_kernel<K, S, WS>, dim3(persistent_grid(p)), dim3(DWT_THREADS), (size_t)p.stages * p.stage_bytes + 128, st,
+                       tm, w_tc, y, p);   // errors: caller's PB_CHECK_LAUNCH
     return true;
 }
 
@@ -605,7 +612,8 @@ static bool launch_dgrad_s2(const __nv_bfloat16* dy, const float* w_tc, __nv_bfl
     if (make_map5(&tm, dy, d.C, d.Wo, d.Ho, d.To, d.B, p.Cb, p.Wi, p.Hi) != PB_OK) return false;
     static std::once_flag once;
     set_smem_once(dw_dgrad_s2_tma_kernel<K, XS>, once);
-    dw_dgrad_s2_tma_kernel<K, XS><<<persistent_grid(p), DWT_THREADS, (size_t)p.stages * p.stage_bytes + 128, st>>>(tm, w_tc, dx, p);
+    (void)launch_pdl(dw_dgrad_s2_tma_kernel<K, XS>, dim3(persistent_grid(p)), dim3(DWT_THREADS), (size_t)p.stages * p.stage_bytes + 128, st,
+                       tm, w_tc, dx, p);
     return true;
 }
 
@@ -624,7 +632,8 @@ static bool launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float*
     if (make_map5(&tmd, dy, d.C, d.Wo, d.Ho, d.To, d.B, p.Cb, p.Wt, p.Ht) != PB_OK) return false;
     static std::once_flag once;
     set_smem_once(dw_wgrad_tma_kernel<K, S, WS>, once);
-    dw_wgrad_tma_kernel<K, S, WS><<<persistent_grid(p), DWT_THREADS, (size_t)p.stages * p.stage_bytes + 128, st>>>(tmx, tmd, dw_tc, p);
+    (void)launch_pdl(dw_wgrad_tma_kernel<K, S, WS>, dim3(persistent_grid(p)), dim3(DWT_THREADS), (size_t)p.stages * p.stage_bytes + 128, st,
+                       tmx, tmd, dw_tc, p);
     return true;
 }
 

@@ -26,6 +26,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double M, co
                                    float* __restrict__ rvar, int training, float momentum, float eps,
                                    float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_o, float* __restrict__ invstd_o, int C) {
+    pdl_trigger();
+    pdl_wait();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float mean, var;
@@ -79,6 +81,8 @@ template <typename T, int ACT>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                   const float* __restrict__ mask, T* __restrict__ out, unsigned M, unsigned R, int C, float slope) {
+    pdl_trigger();
+    pdl_wait();
     const RowLayout L(C);
     if (!L.active) return;
     float sc[8], sh[8];
@@ -133,6 +137,8 @@ bn_bwd_reduce_kernel(const void* __restrict__ dout, const T* __restrict__ z, con
                      const float* __restrict__ shift, const float* __restrict__ mean,
                      const float* __restrict__ invstd, const float* __restrict__ mask, double* __restrict__ sums,
                      unsigned M, unsigned R, int C, float slope) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sm_fold[16 * 256];
     const RowLayout L(C);
     float s[16];
@@ -180,6 +186,8 @@ bn_bwd_reduce_kernel(const void* __restrict__ dout, const T* __restrict__ z, con
 template <typename T>
 __global__ void __launch_bounds__(256)
 colstats_kernel(const T* __restrict__ z, double* __restrict__ sums, unsigned M, int C) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sm_fold[16 * 256];
     const RowLayout L(C);
     float s[16];
@@ -217,6 +225,8 @@ colstats_kernel(const T* __restrict__ z, double* __restrict__ sums, unsigned M, 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double M, int training,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ coef, int C) {
+    pdl_trigger();
+    pdl_wait();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double s0 = 0, s1 = 0;
@@ -234,6 +244,8 @@ bn_bwd_apply_kernel(const void* __restrict__ dout, const T* __restrict__ z, cons
                     const float* __restrict__ shift, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ mask,
                     const float* __restrict__ coef, T* __restrict__ dz, unsigned M, unsigned R, int C, float slope) {
+    pdl_trigger();
+    pdl_wait();
     const RowLayout L(C);
     if (!L.active) return;
     float sc[8], sh[8], a[8], bb[8], k0[8], k1[8];
@@ -287,7 +299,7 @@ extern "C" int pb_colstats(const void* x, int dtype, long long M, int C, double*
     PB_REQUIRE(M < (1LL << 31), "colstats: too many rows");
     const int grid = row_grid(M, C);
     PB_DISPATCH_DTYPE(dtype, {
-        colstats_kernel<T><<<grid, 256, 0, st>>>((const T*)x, sums, (unsigned)M, C);
+        (void)launch_pdl(colstats_kernel<T>, dim3(grid), dim3(256), 0, st, (const T*)x, sums, (unsigned)M, C);
     });
     PB_CHECK_LAUNCH("colstats");
     return PB_OK;
@@ -298,9 +310,7 @@ extern "C" int pb_bn_finalize(const double* sums, long long M, const float* gamm
                               float* scale, float* shift, float* mean, float* invstd, int C, pb_stream_t stream) {
     PB_REQUIRE(scale && shift && C > 0, "bn_finalize: bad args");
     PB_REQUIRE(training ? (sums != nullptr && M > 0) : (running_mean && running_var), "bn_finalize: missing statistics");
-    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, (double)M, gamma, beta, running_mean,
-                                                                        running_var, training, momentum, eps, scale,
-                                                                        shift, mean, invstd, C);
+    (void)launch_pdl(bn_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, (double)M, gamma, beta, running_mean, running_var, training, momentum, eps, scale, shift, mean, invstd, C);
     PB_CHECK_LAUNCH("bn_finalize");
     return PB_OK;
 }
@@ -312,8 +322,7 @@ extern "C" int pb_bn_act_fwd(const void* z, const float* scale, const float* shi
     PB_REQUIRE(M < (1LL << 31) && R < (1LL << 31), "bn_act_fwd: too many rows");
     const int grid = row_grid(M, C);
     PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
-        bn_act_fwd_kernel<T, ACT><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)z, scale, shift, mask, (T*)out,
-                                                                        (unsigned)M, (unsigned)R, C, slope);
+        (void)launch_pdl(bn_act_fwd_kernel<T, ACT>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)z, scale, shift, mask, (T*)out, (unsigned)M, (unsigned)R, C, slope);
     }));
     PB_CHECK_LAUNCH("bn_act_fwd");
     return PB_OK;
@@ -333,11 +342,9 @@ extern "C" int pb_bn_act_bwd_reduce(const void* dout, int dout_bcast, const void
     const size_t smem = 0;
     PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
         if (dout_bcast)
-            bn_bwd_reduce_kernel<T, ACT, true><<<grid, 256, smem, st>>>(dout, (const T*)z, scale, shift, mean, invstd,
-                                                                      mask, sums, (unsigned)M, (unsigned)R, C, slope);
+            (void)launch_pdl(bn_bwd_reduce_kernel<T, ACT, true>, dim3(grid), dim3(256), smem, st, dout, (const T*)z, scale, shift, mean, invstd, mask, sums, (unsigned)M, (unsigned)R, C, slope);
         else
-            bn_bwd_reduce_kernel<T, ACT, false><<<grid, 256, smem, st>>>(dout, (const T*)z, scale, shift, mean, invstd,
-                                                                       mask, sums, (unsigned)M, (unsigned)R, C, slope);
+            (void)launch_pdl(bn_bwd_reduce_kernel<T, ACT, false>, dim3(grid), dim3(256), smem, st, dout, (const T*)z, scale, shift, mean, invstd, mask, sums, (unsigned)M, (unsigned)R, C, slope);
     }));
     PB_CHECK_LAUNCH("bn_act_bwd_reduce");
     return PB_OK;
@@ -346,7 +353,7 @@ extern "C" int pb_bn_act_bwd_reduce(const void* dout, int dout_bcast, const void
 extern "C" int pb_bn_bwd_finalize(const double* sums, long long M, int training, float* dgamma, float* dbeta,
                                   float* coef, int C, pb_stream_t stream) {
     PB_REQUIRE(sums && coef && M > 0 && C > 0, "bn_bwd_finalize: bad args");
-    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, (double)M, training, dgamma, dbeta, coef, C);
+    (void)launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, (double)M, training, dgamma, dbeta, coef, C);
     PB_CHECK_LAUNCH("bn_bwd_finalize");
     return PB_OK;
 }
@@ -363,11 +370,9 @@ extern "C" int pb_bn_act_bwd_apply(const void* dout, int dout_bcast, const void*
     cudaStream_t st = (cudaStream_t)stream;
     PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
         if (dout_bcast)
-            bn_bwd_apply_kernel<T, ACT, true><<<grid, 256, 0, st>>>(dout, (const T*)z, scale, shift, mean, invstd, mask,
-                                                                  coef, (T*)dz, (unsigned)M, (unsigned)R, C, slope);
+            (void)launch_pdl(bn_bwd_apply_kernel<T, ACT, true>, dim3(grid), dim3(256), 0, st, dout, (const T*)z, scale, shift, mean, invstd, mask, coef, (T*)dz, (unsigned)M, (unsigned)R, C, slope);
         else
-            bn_bwd_apply_kernel<T, ACT, false><<<grid, 256, 0, st>>>(dout, (const T*)z, scale, shift, mean, invstd, mask,
-                                                                   coef, (T*)dz, (unsigned)M, (unsigned)R, C, slope);
+            (void)launch_pdl(bn_bwd_apply_kernel<T, ACT, false>, dim3(grid), dim3(256), 0, st, dout, (const T*)z, scale, shift, mean, invstd, mask, coef, (T*)dz, (unsigned)M, (unsigned)R, C, slope);
     }));
     PB_CHECK_LAUNCH("bn_act_bwd_apply");
     return PB_OK;

@@ -16,6 +16,8 @@ gemm_simt_kernel(const T* __restrict__ A, const float* __restrict__ W, long long
                  const float* __restrict__ bias, const float* __restrict__ ascale,
                  const float* __restrict__ colscale, const float* __restrict__ coladd,
                  T* __restrict__ C, long long R, int K, int N) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float As[BK][BM + 4];
     __shared__ float Ws[BK][BN + 4];
     const int b = blockIdx.z;
@@ -86,6 +88,8 @@ __global__ void __launch_bounds__(256)
 wgrad_simt_kernel(const T* __restrict__ A, const T* __restrict__ dC, const float* __restrict__ ascale,
                   float* __restrict__ dW, float* __restrict__ dbias, long long M, long long R, int K, int N,
                   long long rows_per_cta) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float Ds[BK][BN + 4];
     __shared__ float As[BK][BM + 4];
     const int n0 = blockIdx.y * BN, k0 = blockIdx.z * BM;
@@ -151,6 +155,8 @@ wgrad_simt_kernel(const T* __restrict__ A, const T* __restrict__ dC, const float
 template <typename TD>
 __global__ void cast_matrix_kernel(const float* __restrict__ src, TD* __restrict__ dst, int rows, int cols,
                                    int transpose, int round_bf16) {
+    pdl_trigger();
+    pdl_wait();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)rows * cols) return;
     int r = (int)(idx / cols), c = (int)(idx % cols);
@@ -162,6 +168,8 @@ __global__ void cast_matrix_kernel(const float* __restrict__ src, TD* __restrict
 
 __global__ void fold_gate_kernel(const float* __restrict__ W, const float* __restrict__ gate,
                                  __nv_bfloat16* __restrict__ dst, int N, int K, long long total) {
+    pdl_trigger();
+    pdl_wait();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     int k = (int)(idx % K);
@@ -183,8 +191,7 @@ extern "C" int pb_pw_gemm_simt(const void* A, const float* W, long long w_sn, lo
     PB_REQUIRE(Bt <= 65535 && ceil_div(N, BN) <= 65535, "pw_gemm_simt: grid too large");
     dim3 grid(ceil_div(R, BM), ceil_div(N, BN), Bt);
     PB_DISPATCH_DTYPE(dtype, {
-        gemm_simt_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)A, W, w_sn, w_sk, bias, ascale,
-                                                                  colscale, coladd, (T*)C, R, K, N);
+        (void)launch_pdl(gemm_simt_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)A, W, w_sn, w_sk, bias, ascale, colscale, coladd, (T*)C, R, K, N);
     });
     PB_CHECK_LAUNCH("gemm_simt_kernel");
     return PB_OK;
@@ -204,7 +211,7 @@ extern "C" int pb_pw_wgrad_simt(const void* A, const void* dC, const float* asca
     rows = (rows + BK - 1) / BK * BK;
     dim3 grid(ceil_div(M, rows), ceil_div(N, BN), ceil_div(K, BM));
     PB_DISPATCH_DTYPE(dtype, {
-        wgrad_simt_kernel<T><<<grid, 256, 0, st>>>((const T*)A, (const T*)dC, ascale, dW, dbias, M, R, K, N, rows);
+        (void)launch_pdl(wgrad_simt_kernel<T>, dim3(grid), dim3(256), 0, st, (const T*)A, (const T*)dC, ascale, dW, dbias, M, R, K, N, rows);
     });
     PB_CHECK_LAUNCH("wgrad_simt_kernel");
     return PB_OK;
@@ -216,11 +223,11 @@ extern "C" int pb_cast_matrix(const float* src, void* dst, int dst_dtype, int ro
     long long n = (long long)rows * cols;
     cudaStream_t st = (cudaStream_t)stream;
     if (dst_dtype == PB_BF16)
-        cast_matrix_kernel<__nv_bfloat16><<<ceil_div(n, 256), 256, 0, st>>>(src, (__nv_bfloat16*)dst, rows, cols, transpose, 0);
+        (void)launch_pdl(cast_matrix_kernel<__nv_bfloat16>, dim3(ceil_div(n, 256)), dim3(256), 0, st, src, (__nv_bfloat16*)dst, rows, cols, transpose, 0);
     else if (dst_dtype == PB_F32)
-        cast_matrix_kernel<float><<<ceil_div(n, 256), 256, 0, st>>>(src, (float*)dst, rows, cols, transpose, 0);
+        (void)launch_pdl(cast_matrix_kernel<float>, dim3(ceil_div(n, 256)), dim3(256), 0, st, src, (float*)dst, rows, cols, transpose, 0);
     else if (dst_dtype == PB_F32_RBF16)   // fp32 storage, values rounded through bf16 (autocast's weight cast)
-        cast_matrix_kernel<float><<<ceil_div(n, 256), 256, 0, st>>>(src, (float*)dst, rows, cols, transpose, 1);
+        (void)launch_pdl(cast_matrix_kernel<float>, dim3(ceil_div(n, 256)), dim3(256), 0, st, src, (float*)dst, rows, cols, transpose, 1);
     else { set_error("cast_matrix: bad dst dtype %d", dst_dtype); return PB_ERR_BAD_ARG; }
     PB_CHECK_LAUNCH("cast_matrix_kernel");
     return PB_OK;
@@ -230,7 +237,7 @@ extern "C" int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, i
                                  pb_stream_t stream) {
     PB_REQUIRE(W && gate && dst && Bt > 0 && N > 0 && K > 0, "fold_gate: bad args");
     long long n = (long long)Bt * N * K;
-    fold_gate_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(W, gate, (__nv_bfloat16*)dst, N, K, n);
+    (void)launch_pdl(fold_gate_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, W, gate, (__nv_bfloat16*)dst, N, K, n);
     PB_CHECK_LAUNCH("fold_gate_kernel");
     return PB_OK;
 }

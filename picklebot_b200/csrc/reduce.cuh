@@ -36,6 +36,8 @@ __device__ __forceinline__ void cta_fold_rows(float (&acc)[NACC], int G, int RPI
 template <typename F, int NV, typename OUT>
 __global__ void __launch_bounds__(256)
 colreduce_kernel(F f, long long R, int C, OUT* __restrict__ out, int nbatch, float out_scale) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sm_fold[NV * 8 * 256];
     const int G = C >> 3;
     const int RPI = blockDim.x / G;

@@ -25,6 +25,8 @@ template <int ACT>
 __global__ void __launch_bounds__(256)
 fc_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
                float* __restrict__ Y, int B, int N, int K) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float xs[];                       // [FC_BT][K]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b0 = blockIdx.y * FC_BT;
@@ -69,6 +71,8 @@ fc_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, const f
 __global__ void __launch_bounds__(256)
 fc_cols_kernel(const float* __restrict__ X, const float* __restrict__ Wt, const float* __restrict__ relu_ref,
                float* __restrict__ Y, int B, int N, int K, float scale) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float xs[];                       // [FC_BT][K] | red[8][FC_BT][33]
     float* red = xs + FC_BT * K;
     const int nl = threadIdx.x & 31, ks = threadIdx.x >> 5;
@@ -104,6 +108,8 @@ fc_cols_kernel(const float* __restrict__ X, const float* __restrict__ Wt, const 
 // da2 = dgate * hardsigmoid'(.) : 1/6 where 0 < gate < 1
 __global__ void hsig_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ gate,
                                 float* __restrict__ da2, long long n) {
+    pdl_trigger();
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float g = gate[i];
@@ -115,6 +121,8 @@ __global__ void se_fc_bwd_param_kernel(const float* __restrict__ a2, const float
                                        const float* __restrict__ mean, const float* __restrict__ hidden,
                                        float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
                                        float* __restrict__ db2, int B, int C, int Ch) {
+    pdl_trigger();
+    pdl_wait();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long nW = (long long)C * Ch;
     if (idx < nW) {                       // dW2[c][j] = sum_b da2[b][c] * hidden[b][j]
@@ -151,10 +159,10 @@ extern "C" int pb_se_fc_fwd(const float* mean, const float* W1, const float* b1,
     cudaStream_t st = (cudaStream_t)stream;
     PB_REQUIRE(C <= 1536 && Ch <= 1536, "se_fc_fwd: channel count too large for the shared-memory staging");
     dim3 g1(ceil_div(Ch, 32), ceil_div(B, FC_BT));
-    fc_rows_kernel<PB_ACT_RELU><<<g1, 256, sizeof(float) * FC_BT * C, st>>>(mean, W1, b1, hidden, B, Ch, C);
+    (void)launch_pdl(fc_rows_kernel<PB_ACT_RELU>, dim3(g1), dim3(256), sizeof(float) * FC_BT * C, st, mean, W1, b1, hidden, B, Ch, C);
     PB_CHECK_LAUNCH("se_fc_fwd(1)");
     dim3 g2(ceil_div(C, 32), ceil_div(B, FC_BT));
-    fc_rows_kernel<PB_ACT_HSIGMOID><<<g2, 256, sizeof(float) * FC_BT * Ch, st>>>(hidden, W2, b2, gate, B, C, Ch);
+    (void)launch_pdl(fc_rows_kernel<PB_ACT_HSIGMOID>, dim3(g2), dim3(256), sizeof(float) * FC_BT * Ch, st, hidden, W2, b2, gate, B, C, Ch);
     PB_CHECK_LAUNCH("se_fc_fwd(2)");
     return PB_OK;
 }
@@ -170,20 +178,20 @@ extern "C" int pb_se_fc_bwd(const float* dgate, const float* mean, const float* 
     float* a2 = work;                          // [B][C]
     float* a1 = work + (long long)B * C;       // [B][Ch]
     const long long nBC = (long long)B * C;
-    hsig_bwd_kernel<<<ceil_div(nBC, 256), 256, 0, st>>>(dgate, gate, a2, nBC);
+    (void)launch_pdl(hsig_bwd_kernel, dim3(ceil_div(nBC, 256)), dim3(256), 0, st, dgate, gate, a2, nBC);
     PB_CHECK_LAUNCH("se_fc_bwd(hsig)");
     // da1[b][j] = relu'(hidden) * sum_c da2[b][c] * W2[c][j]   (W2 is [C][Ch] = "Wt" with K=C, N=Ch)
     dim3 g1(ceil_div(Ch, 32), ceil_div(B, FC_BT));
     PB_REQUIRE(C <= 1200 && Ch <= 1200, "se_fc_bwd: channel count too large for the shared-memory staging");
     const size_t red_bytes = sizeof(float) * 8 * FC_BT * 33;
-    fc_cols_kernel<<<g1, 256, sizeof(float) * FC_BT * C + red_bytes, st>>>(a2, W2, hidden, a1, B, Ch, C, 1.f);
+    (void)launch_pdl(fc_cols_kernel, dim3(g1), dim3(256), sizeof(float) * FC_BT * C + red_bytes, st, a2, W2, hidden, a1, B, Ch, C, 1.f);
     PB_CHECK_LAUNCH("se_fc_bwd(da1)");
     // dmean[b][c] = inv_R * sum_j da1[b][j] * W1[j][c]         (W1 is [Ch][C] = "Wt" with K=Ch, N=C)
     dim3 g2(ceil_div(C, 32), ceil_div(B, FC_BT));
-    fc_cols_kernel<<<g2, 256, sizeof(float) * FC_BT * Ch + red_bytes, st>>>(a1, W1, nullptr, dmean, B, C, Ch, inv_R);
+    (void)launch_pdl(fc_cols_kernel, dim3(g2), dim3(256), sizeof(float) * FC_BT * Ch + red_bytes, st, a1, W1, nullptr, dmean, B, C, Ch, inv_R);
     PB_CHECK_LAUNCH("se_fc_bwd(dmean)");
     long long n = 2LL * C * Ch + C + Ch;
-    se_fc_bwd_param_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a2, a1, mean, hidden, dW1, db1, dW2, db2, B, C, Ch);
+    (void)launch_pdl(se_fc_bwd_param_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, a2, a1, mean, hidden, dW1, db1, dW2, db2, B, C, Ch);
     PB_CHECK_LAUNCH("se_fc_bwd(param)");
     return PB_OK;
 }

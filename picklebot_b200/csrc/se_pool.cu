@@ -29,6 +29,8 @@ template <typename T, bool ADD>
 __global__ void __launch_bounds__(256)
 rowscale_kernel(const T* x, const float* __restrict__ gate, const float* __restrict__ add,
                 T* y, long long R, int C, long long total) {   // x may alias y (in-place)
+    pdl_trigger();
+    pdl_wait();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int G = C >> 3;
@@ -57,7 +59,7 @@ extern "C" int pb_pool_fwd(const void* x, int dtype, int B, long long R, int C, 
     dim3 grid = colreduce_grid(R, C, B);
     PB_DISPATCH_DTYPE(dtype, {
         PoolF<T> f{(const T*)x, R, C};
-        colreduce_kernel<PoolF<T>, 1, float><<<grid, 256, 0, st>>>(f, R, C, mean, B, 1.f / (float)R);
+        (void)launch_pdl(colreduce_kernel<PoolF<T>, 1, float>, dim3(grid), dim3(256), 0, st, f, R, C, mean, B, 1.f / (float)R);
     });
     PB_CHECK_LAUNCH("pool_fwd");
     return PB_OK;
@@ -71,7 +73,7 @@ extern "C" int pb_rowdot(const void* g, const void* y, int dtype, int B, long lo
     dim3 grid = colreduce_grid(R, C, B);
     PB_DISPATCH_DTYPE(dtype, {
         DotF<T> f{(const T*)g, (const T*)y, R, C};
-        colreduce_kernel<DotF<T>, 1, float><<<grid, 256, 0, st>>>(f, R, C, out, B, 1.f);
+        (void)launch_pdl(colreduce_kernel<DotF<T>, 1, float>, dim3(grid), dim3(256), 0, st, f, R, C, out, B, 1.f);
     });
     PB_CHECK_LAUNCH("rowdot");
     return PB_OK;
@@ -82,7 +84,7 @@ extern "C" int pb_rowscale(const void* x, const float* gate, void* y, int dtype,
     PB_REQUIRE(x && gate && y && B > 0 && R > 0 && C > 0 && C % 8 == 0, "rowscale: bad args");
     long long total = (long long)B * R * (C / 8);
     PB_DISPATCH_DTYPE(dtype, {
-        rowscale_kernel<T, false><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, gate, nullptr, (T*)y, R, C, total);
+        (void)launch_pdl(rowscale_kernel<T, false>, dim3(ceil_div(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, gate, nullptr, (T*)y, R, C, total);
     });
     PB_CHECK_LAUNCH("rowscale");
     return PB_OK;
@@ -93,7 +95,7 @@ extern "C" int pb_scale_add(void* g, const float* gate, const float* add, int dt
     PB_REQUIRE(g && gate && add && B > 0 && R > 0 && C > 0 && C % 8 == 0, "scale_add: bad args");
     long long total = (long long)B * R * (C / 8);
     PB_DISPATCH_DTYPE(dtype, {
-        rowscale_kernel<T, true><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)g, gate, add, (T*)g, R, C, total);
+        (void)launch_pdl(rowscale_kernel<T, true>, dim3(ceil_div(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const T*)g, gate, add, (T*)g, R, C, total);
     });
     PB_CHECK_LAUNCH("scale_add");
     return PB_OK;
