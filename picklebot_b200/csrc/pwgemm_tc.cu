@@ -1,5 +1,6 @@
 // Pointwise-conv GEMMs on the 5th-generation tensor cores: TMA -> 128B-swizzled shared memory ->
-// tcgen05.mma (one elected thread) -> fp32 accumulators in TMEM -> tcgen05.ld epilogue -> bf16 stores.
+// tcgen05.mma (one elected thread) -> fp32 accumulators in TMEM -> tcgen05.ld epilogue -> bf16, staged per warp through swizzled shared memory so
+// that the global stores are row-contiguous.
 //
 //   C[b][r][n] = (sum_k A[b][r][k] * W[bw][n][k] + bias[n]) * colscale[b][n] + coladd[b][n]
 //
@@ -40,6 +41,8 @@ EncodeTiledFn encode_fn() {
 constexpr int BM = 128;
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
+constexpr int EPI_STAGE_BYTES = 32 * 128;     // per epilogue warp: 32 rows x one 64-column bf16 panel
+constexpr int RING_BYTES = 190 * 1024;         // TMA ring budget (+ 8 staging panels + alignment <= 226 KB)
 
 struct GemmParams {
     int Bt, K, N, Bw;
@@ -61,6 +64,7 @@ __device__ __forceinline__ void ldg16(const float* p, float (&v)[16]) {
     }
 }
 
+template <bool EPI>      // EPI: any of bias / colscale / coladd present
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -144,6 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // tile, so the TMEM loads / conversions / stores of consecutive tiles overlap
         const int q = warp & 3;
         const int group = (warp - 4) >> 2;
+        uint8_t* stage_w = tiles + (size_t)p.stages * stage_bytes + (size_t)(warp - 4) * EPI_STAGE_BYTES;
         long long it = 0;
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int a = (int)(it & 1);
@@ -158,47 +163,87 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tfull_bar[a], aph);
             tc_fence_after();
             for (int sub = 0; sub < p.mt; ++sub) {
-                const long long row = ((long long)m_tile * p.mt + sub) * BM + q * 32 + lane;
-                const bool row_ok = row < p.R;
-                __nv_bfloat16* crow = p.C + ((long long)b * p.R + row) * p.N;
+                const long long row0 = ((long long)m_tile * p.mt + sub) * BM + q * 32;     // first row of this warp
+                __nv_bfloat16* cbase = p.C + ((long long)b * p.R + row0) * p.N;
+                const int rows_ok = (int)max(0LL, min(32LL, p.R - row0));
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_cols + sub * p.block_n);
-                for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(taddr + (uint32_t)c0, r);
+                // 64-column panels: TMEM -> registers -> this warp's swizzled staging rows -> coalesced stores
+                // (a lane owns a row in TMEM; storing rows directly would touch 32 lines per instruction)
+                for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+                    const int pw = min(64, p.block_n - c0);                                 // 16, 32, 48 or 64
+                    uint32_t r[4][16];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        if (g * 16 < pw) tmem_ld16(taddr + (uint32_t)(c0 + g * 16), r[g]);
                     tmem_ld_wait();
-                    const int n0 = n_base + c0;
-                    if (row_ok && n0 < p.N) {
-                        float v[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                        const bool full16 = n0 + 16 <= p.N;        // else exactly 8 valid (N % 8 == 0)
-                        if (full16) {
-                            float e[16];
-                            if (p.bias) { ldg16(p.bias + n0, e);
+                    for (int g = 0; g < 4; ++g) {
+                        const int n0 = n_base + c0 + g * 16;
+                        if (g * 16 < pw && n0 < p.N) {
+                            float v[16];
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] += e[j]; }
-                            if (cs) { ldg16(cs + n0, e);
+                            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[g][j]);
+                            if (EPI) {
+                                if (n0 + 16 <= p.N) {
+                                    float e[16];
+                                    if (p.bias) { ldg16(p.bias + n0, e);
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] *= e[j]; }
-                            if (ca) { ldg16(ca + n0, e);
+                                        for (int j = 0; j < 16; ++j) v[j] += e[j]; }
+                                    if (cs) { ldg16(cs + n0, e);
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] += e[j]; }
-                        } else {
+                                        for (int j = 0; j < 16; ++j) v[j] *= e[j]; }
+                                    if (ca) { ldg16(ca + n0, e);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                if (p.bias) v[j] += __ldg(p.bias + n0 + j);
-                                if (cs) v[j] *= __ldg(cs + n0 + j);
-                                if (ca) v[j] += __ldg(ca + n0 + j);
+                                        for (int j = 0; j < 16; ++j) v[j] += e[j]; }
+                                } else {                               // exactly 8 valid columns (N % 8 == 0)
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        if (p.bias) v[j] += __ldg(p.bias + n0 + j);
+                                        if (cs) v[j] *= __ldg(cs + n0 + j);
+                                        if (ca) v[j] += __ldg(ca + n0 + j);
+                                    }
+                                }
+                            }
+                            uint4 o0, o1;
+                            o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+                            o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+                            o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+                            o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+                            uint8_t* rowp = stage_w + lane * 128;
+                            *reinterpret_cast<uint4*>(rowp + (((2 * g) ^ (lane & 7)) << 4)) = o0;
+                            *reinterpret_cast<uint4*>(rowp + (((2 * g + 1) ^ (lane & 7)) << 4)) = o1;
+                        }
+                    }
+                    __syncwarp();
+                    if (pw == 64) {                                    // 8 chunks per row: 4 rows per instruction
+                        const int ch = lane & 7, r4 = lane >> 3;
+                        const int col = n_base + c0 + ch * 8;
+                        uint4 v4[8];
+#pragma unroll
+                        for (int s8 = 0; s8 < 8; ++s8) {
+                            const int rr = s8 * 4 + r4;
+                            v4[s8] = *reinterpret_cast<const uint4*>(stage_w + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                        }
+                        if (col < p.N) {
+#pragma unroll
+                            for (int s8 = 0; s8 < 8; ++s8) {
+                                const int rr = s8 * 4 + r4;
+                                if (rr < rows_ok) *reinterpret_cast<uint4*>(cbase + (long long)rr * p.N + col) = v4[s8];
                             }
                         }
-                        uint4 o0, o1;
-                        o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
-                        o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
-                        o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
-                        o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-                        *reinterpret_cast<uint4*>(crow + n0) = o0;
-                        if (full16) *reinterpret_cast<uint4*>(crow + n0 + 8) = o1;
+                    } else {
+                        const int cpr = pw >> 3;                       // 2, 4 or 6 sixteen-byte chunks per row
+                        const uint32_t inv = 65536u / (uint32_t)cpr + 1u;   // exact floor(L / cpr) for L < 256
+                        for (int L = lane; L < 32 * cpr; L += 32) {
+                            const int rr = (int)(((uint32_t)L * inv) >> 16), ch = L - rr * cpr;
+                            const int col = n_base + c0 + ch * 8;
+                            if (rr < rows_ok && col < p.N) {
+                                const uint4 v4 = *reinterpret_cast<const uint4*>(stage_w + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                                *reinterpret_cast<uint4*>(cbase + (long long)rr * p.N + col) = v4;
+                            }
+                        }
                     }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -243,15 +288,15 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     if (p.n_tiles == 1 && p.k_chunks <= 4) {
         p.mt = std::min(4, 256 / p.block_n);
         p.mt = (int)std::max<long long>(1, std::min<long long>(p.mt, (R + BM - 1) / BM));
-        while (p.mt > 1 && (200 * 1024) / ((p.mt * BM + p.block_n) * BK * 2) < 3) --p.mt;   // keep >= 3 stages
+        while (p.mt > 1 && RING_BYTES / ((p.mt * BM + p.block_n) * BK * 2) < 3) --p.mt;   // keep >= 3 stages
     }
     p.m_tiles = ceil_div(R, (long long)BM * p.mt);
     p.total_tiles = (long long)Bt * p.m_tiles * p.n_tiles;
     const int stage_bytes = (p.mt * BM + p.block_n) * BK * 2;
-    p.stages = std::min(MAX_STAGES, (200 * 1024) / stage_bytes);
+    p.stages = std::min(MAX_STAGES, RING_BYTES / stage_bytes);
     PB_REQUIRE(p.stages >= 2, "pw_gemm_tc: internal tiling error");
     p.bias = bias; p.colscale = colscale; p.coladd = coladd; p.C = (__nv_bfloat16*)C;
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    const size_t smem = (size_t)p.stages * stage_bytes + 8 * EPI_STAGE_BYTES + 1024;
 
     CUtensorMap tmA, tmW;
     {
@@ -269,14 +314,19 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        attr_err = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(gemm_tc_kernel)");
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = (int)std::min<long long>(p.total_tiles, sms);
-    PB_CUDA(launch_pdl(gemm_tc_kernel, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
+    if (bias || colscale || coladd)
+        PB_CUDA(launch_pdl(gemm_tc_kernel<true>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
+    else
+        PB_CUDA(launch_pdl(gemm_tc_kernel<false>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
     PB_CHECK_LAUNCH("gemm_tc_kernel");
     return PB_OK;
 }
