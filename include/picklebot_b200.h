@@ -110,6 +110,10 @@ int pb_cast_matrix(const float* src, void* dst, int dst_dtype, int rows, int col
                    pb_stream_t stream);
 /* dst[b][n][k] = bf16( W[n][k] * gate[b][k] )  -- squeeze-excite gate folded into pointwise_conv2. */
 int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, int Bt, int N, int K, pb_stream_t stream);
+/* dst bf16 [F*N][F*K] = diag(W, ..., W) for W bf16 [N][K]: the weight of a row-folded GEMM.  A layer with
+ * K <= 32 input channels is run as X'[rows/F][F*K] x dst^T = C'[rows/F][F*N], which is C[rows][N] in memory,
+ * so that TMA moves 128-byte rows instead of 32-byte ones. */
+int pb_block_diag_bf16(const void* W, void* dst, int F, int N, int K, pb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm3d/1d (+ activation + Dropout3d) -- mobilenet.py:80-82,90-92,142-143,180-181,247-248;

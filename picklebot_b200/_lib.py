@@ -32,6 +32,7 @@ SIGNATURES = {
     "pb_pw_wgrad_tc": "pppppppiliip",
     "pb_cast_matrix": "ppiiiip",
     "pb_fold_gate_bf16": "pppiiip",
+    "pb_block_diag_bf16": "ppiiip",
     "pb_colstats": "pilipp",
     "pb_bn_finalize": "plppppiffppppip",
     "pb_bn_act_fwd": "pppppiiliifp",

@@ -93,6 +93,16 @@ def _w2d(w: torch.Tensor) -> torch.Tensor:
     return w.detach().reshape(w.shape[0], -1)
 
 
+def _row_fold(rows: int, K: int) -> int:
+    """Row-fold factor for a GEMM whose reduction dimension K is 16..32 channels wide.  A TMA box row costs the
+    same whether it carries 32 or 128 bytes, so X[rows][K] is streamed as X'[rows/F][F*K] against the block-diagonal
+    weight diag(W, ..., W); the output C'[rows/F][F*N] is C[rows][N] byte for byte."""
+    F = 4 if K <= 16 else 2 if K <= 32 else 1
+    while F > 1 and rows % F:
+        F //= 2
+    return F
+
+
 def pw_fwd(A: torch.Tensor, w: torch.Tensor, cache: WeightCache, key: str, bias=None, gate=None, Bt: int = 1
            ) -> torch.Tensor:
     """[rows][K] x W[N][K]^T (+bias); gate [Bt][K] scales A's columns per sample (squeeze-excite)."""
@@ -103,6 +113,10 @@ def pw_fwd(A: torch.Tensor, w: torch.Tensor, cache: WeightCache, key: str, bias=
             Wb = ops.fold_gate(W, gate)
             return gemm_tc.gemm(A, Wb, N, K, Bw=Bt, Bt=Bt, bias=bias)
         Wb = cache.get((key, "bf16"), w, lambda: ops.cast_matrix(W, N, K, torch.bfloat16))
+        F = _row_fold(A.numel() // K, K) if bias is None else 1
+        if F > 1:
+            Wf = cache.get((key, "bf16", F), w, lambda: ops.block_diag(Wb, F))
+            return gemm_tc.gemm(A, Wf, N * F, K * F).view(-1, N)
         return gemm_tc.gemm(A, Wb, N, K, Bw=1, Bt=1, bias=bias)
     return ops.gemm_simt(A, W, N, K, K, 1, bias=bias, ascale=gate, Bt=Bt)
 
@@ -113,6 +127,10 @@ def pw_dgrad(dC: torch.Tensor, w: torch.Tensor, cache: WeightCache, key: str) ->
     N, K = W.shape
     if ops.use_tc(dC.dtype, N, K):
         Wt = cache.get((key, "bf16_t"), w, lambda: ops.cast_matrix(W, N, K, torch.bfloat16, transpose=True))
+        F = _row_fold(dC.numel() // N, N)
+        if F > 1:
+            Wf = cache.get((key, "bf16_t", F), w, lambda: ops.block_diag(Wt, F))
+            return gemm_tc.gemm(dC, Wf, K * F, N * F).view(-1, K)
         return gemm_tc.gemm(dC, Wt, K, N, Bw=1, Bt=1)
     return ops.gemm_simt(dC, W, K, N, 1, K)
 

@@ -179,6 +179,19 @@ __global__ void fold_gate_kernel(const float* __restrict__ W, const float* __res
     dst[idx] = __float2bfloat16_rn(W[(long long)n * K + k] * gate[(long long)b * K + k]);
 }
 
+// dst[(i*N + n)][(j*K + k)] = (i == j) ? W[n][k] : 0  -- the weight of a row-folded GEMM (pwgemm_tc.cu)
+__global__ void block_diag_kernel(const __nv_bfloat16* __restrict__ W, __nv_bfloat16* __restrict__ dst, int F, int N,
+                                  int K, long long total) {
+    pdl_trigger();
+    pdl_wait();
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int col = (int)(idx % ((long long)F * K));
+    const int row = (int)(idx / ((long long)F * K));
+    const int i = row / N, j = col / K;
+    dst[idx] = i == j ? W[(long long)(row - i * N) * K + (col - j * K)] : __float2bfloat16_rn(0.f);
+}
+
 }  // namespace pb
 
 using namespace pb;
@@ -239,5 +252,14 @@ extern "C" int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, i
     long long n = (long long)Bt * N * K;
     (void)launch_pdl(fold_gate_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, W, gate, (__nv_bfloat16*)dst, N, K, n);
     PB_CHECK_LAUNCH("fold_gate_kernel");
+    return PB_OK;
+}
+
+extern "C" int pb_block_diag_bf16(const void* W, void* dst, int F, int N, int K, pb_stream_t stream) {
+    PB_REQUIRE(W && dst && F > 0 && N > 0 && K > 0, "block_diag: bad args");
+    long long n = (long long)F * N * F * K;
+    (void)launch_pdl(block_diag_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream,
+                     (const __nv_bfloat16*)W, (__nv_bfloat16*)dst, F, N, K, n);
+    PB_CHECK_LAUNCH("block_diag_kernel");
     return PB_OK;
 }

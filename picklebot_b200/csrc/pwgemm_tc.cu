@@ -167,6 +167,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __nv_bfloat16* cbase = p.C + ((long long)b * p.R + row0) * p.N;
                 const int rows_ok = (int)max(0LL, min(32LL, p.R - row0));
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_cols + sub * p.block_n);
+                if (EPI) {
+                    // Epilogue vectors present: 32-column fp32 panels.  After the transpose through the staging
+                    // rows a lane owns 4 fixed columns, so bias / colscale / coladd are 3 vector loads per panel
+                    // instead of 12 per row, and the arithmetic still runs on the unrounded fp32 accumulators.
+                    for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+                        const int pw = min(32, p.block_n - c0);                             // 16 or 32
+                        uint32_t r[2][16];
+#pragma unroll
+                        for (int g = 0; g < 2; ++g)
+                            if (g * 16 < pw) tmem_ld16(taddr + (uint32_t)(c0 + g * 16), r[g]);
+                        tmem_ld_wait();
+                        uint8_t* rowp = stage_w + lane * 128;
+#pragma unroll
+                        for (int g = 0; g < 2; ++g)
+                            if (g * 16 < pw) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    *reinterpret_cast<uint4*>(rowp + (((4 * g + j) ^ (lane & 7)) << 4)) =
+                                        make_uint4(r[g][4 * j], r[g][4 * j + 1], r[g][4 * j + 2], r[g][4 * j + 3]);
+                            }
+                        __syncwarp();
+                        const int sh = pw == 32 ? 3 : 2;                                   // 8 or 4 chunks per row
+                        const int ch = lane & ((1 << sh) - 1), r0 = lane >> sh, rstep = 32 >> sh;
+                        const int col = n_base + c0 + ch * 4;
+                        if (col < p.N) {
+                            float4 vb = make_float4(0.f, 0.f, 0.f, 0.f), vs = make_float4(1.f, 1.f, 1.f, 1.f), va = vb;
+                            if (p.bias) vb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                            if (cs) vs = __ldg(reinterpret_cast<const float4*>(cs + col));
+                            if (ca) va = __ldg(reinterpret_cast<const float4*>(ca + col));
+                            for (int rr = r0; rr < rows_ok; rr += rstep) {
+                                const float4 x = *reinterpret_cast<const float4*>(stage_w + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                                uint2 o;
+                                o.x = pack_bf16x2(fmaf(x.x + vb.x, vs.x, va.x), fmaf(x.y + vb.y, vs.y, va.y));
+                                o.y = pack_bf16x2(fmaf(x.z + vb.z, vs.z, va.z), fmaf(x.w + vb.w, vs.w, va.w));
+                                *reinterpret_cast<uint2*>(cbase + (long long)rr * p.N + col) = o;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    continue;
+                }
                 // 64-column panels: TMEM -> registers -> this warp's swizzled staging rows -> coalesced stores
                 // (a lane owns a row in TMEM; storing rows directly would touch 32 lines per instruction)
                 for (int c0 = 0; c0 < p.block_n; c0 += 64) {
@@ -183,27 +224,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float v[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[g][j]);
-                            if (EPI) {
-                                if (n0 + 16 <= p.N) {
-                                    float e[16];
-                                    if (p.bias) { ldg16(p.bias + n0, e);
-#pragma unroll
-                                        for (int j = 0; j < 16; ++j) v[j] += e[j]; }
-                                    if (cs) { ldg16(cs + n0, e);
-#pragma unroll
-                                        for (int j = 0; j < 16; ++j) v[j] *= e[j]; }
-                                    if (ca) { ldg16(ca + n0, e);
-#pragma unroll
-                                        for (int j = 0; j < 16; ++j) v[j] += e[j]; }
-                                } else {                               // exactly 8 valid columns (N % 8 == 0)
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        if (p.bias) v[j] += __ldg(p.bias + n0 + j);
-                                        if (cs) v[j] *= __ldg(cs + n0 + j);
-                                        if (ca) v[j] += __ldg(ca + n0 + j);
-                                    }
-                                }
-                            }
                             uint4 o0, o1;
                             o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
                             o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);

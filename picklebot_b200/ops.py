@@ -94,6 +94,15 @@ def dw_weight_grad_from_tapmajor(dw_tc: torch.Tensor, shape) -> torch.Tensor:
     return cast_matrix(dw_tc, taps, C, torch.float32, transpose=True).view(shape)
 
 
+def block_diag(Wb: torch.Tensor, F: int) -> torch.Tensor:
+    """bf16 [N][K] -> bf16 [F*N][F*K] = diag(W, ..., W) (weights of a row-folded GEMM)."""
+    _chk(Wb, "block_diag.W")
+    N, K = Wb.shape
+    dst = torch.empty((F * N, F * K), dtype=torch.bfloat16, device=Wb.device)
+    call("pb_block_diag_bf16", Wb.data_ptr(), dst.data_ptr(), F, N, K, _st())
+    return dst
+
+
 def fold_gate(W: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
     """bf16 [B][N][K] = W[n][k] * gate[b][k]."""
     N, K = W.shape[0], W.shape[1]

@@ -48,6 +48,21 @@ def test_gemm_tc_per_sample_weights(case):
     assert rel_err(C.float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("case", [(4000, 16, 16, 4), (4000, 16, 64, 4), (1002, 24, 72, 2), (6000, 32, 96, 2)])
+def test_gemm_tc_row_folded(case):
+    """K <= 32 layers run as X'[rows/F][F*K] against diag(W, ..., W) (pb_block_diag_bf16): same bytes out."""
+    from picklebot_b200 import gemm_tc, ops
+    rows, K, N, F = case
+    A = rnd(rows, K, seed=1).bfloat16()
+    W = rnd(N, K, seed=2, scale=0.3).bfloat16()
+    Wf = ops.block_diag(W, F)
+    assert torch.equal(Wf.float(), torch.block_diag(*([W.float()] * F)))
+    C = gemm_tc.gemm(A, Wf, N * F, K * F).view(-1, N)
+    # zero blocks add exact zeros, but the MMA groups the K terms differently: agreement to bf16 round-off
+    assert rel_err(C.float(), gemm_tc.gemm(A, W, N, K).float()) < 3e-3
+    assert rel_err(C.float(), A.float() @ W.float().t()) < 6e-3
+
+
 def test_gemm_tc_matches_simt_bitwise_scale():
     """Same operands through the CUDA-core kernel: both accumulate in fp32, so they agree to bf16 round-off."""
     from picklebot_b200 import gemm_tc, ops
