@@ -154,6 +154,10 @@ int pb_bn_act_bwd_apply(const void* dout, int dout_bcast, const void* z, const f
  * classifiers (mobilenet.py:186, 252; movinet.py:147).
  * ---------------------------------------------------------------------------------------------- */
 int pb_pool_fwd(const void* x, int dtype, int B, long long R, int C, float* mean, pb_stream_t stream);
+/* Classifier-head linear layers (nn.Linear, mobilenet.py:184-190,250-256; movinet.py:146-154), fp32:
+ * Y[b][n] = bias[n] + sum_k X[b][k] W[n][k]   and   dX[b][k] = scale * sum_n dY[b][n] W[n][k]. */
+int pb_fc_fwd(const float* X, const float* W, const float* bias, float* Y, int B, int N, int K, pb_stream_t stream);
+int pb_fc_dgrad(const float* dY, const float* W, float* dX, int B, int N, int K, float scale, pb_stream_t stream);
 /* hidden = relu(W1 mean + b1) [B][Ch];  gate = hardsigmoid(W2 hidden + b2) [B][C]. */
 int pb_se_fc_fwd(const float* mean, const float* W1, const float* b1, const float* W2, const float* b2,
                  float* hidden, float* gate, int B, int C, int Ch, pb_stream_t stream);

@@ -40,6 +40,8 @@ SIGNATURES = {
     "pb_bn_bwd_finalize": "plipppip",
     "pb_bn_act_bwd_apply": "pipppppppp" + "iiliifp",
     "pb_pool_fwd": "piilipp",
+    "pb_fc_fwd": "ppppiiip",
+    "pb_fc_dgrad": "pppiiifp",
     "pb_se_fc_fwd": "pppppppiiip",
     "pb_se_fc_bwd": "ppppppfpppppp" + "iiip",
     "pb_rowscale": "pppiilip",

@@ -305,11 +305,11 @@ class MobileNetTailFn(torch.autograd.Function):
                                  hs, 0.0, None)
         feat = ops.pool_fwd(a, B, Cmid)                                   # fp32 [B][Cmid]
         F1, NC = wf1.shape[0], wf2.shape[0]
-        u1 = ops.gemm_simt(feat, _w2d(wf1), F1, Cmid, Cmid, 1, bias=bf1.detach())
+        u1 = ops.fc_fwd(feat, _w2d(wf1), bf1.detach())
         ones = torch.ones(F1, dtype=torch.float32, device=x.device)
         zeros = torch.zeros(F1, dtype=torch.float32, device=x.device)
         h1 = ops.bn_act_fwd(u1, ones, zeros, None, B, F1, hs)
-        logits = ops.gemm_simt(h1, _w2d(wf2), NC, F1, F1, 1, bias=bf2.detach())
+        logits = ops.fc_fwd(h1, _w2d(wf2), bf2.detach())
         ctx.cache, ctx.training, ctx.use_se = cache, training, use_se
         ctx.shapes = (B, T, H, W, Cin, Cmid, R, F1, NC)
         ctx.save_for_backward(x5, z0, z, pooled, hidden, gate, *bn_state, feat, u1, h1, ones, zeros,
@@ -325,11 +325,10 @@ class MobileNetTailFn(torch.autograd.Function):
         hs = ACT_CODES["hswish"]
         dl = dlogits.contiguous().float()
         dwf2, dbf2 = ops.wgrad_simt(h1, dl, F1, NC, want_bias=True)
-        dh1 = ops.gemm_simt(dl, _w2d(wf2), F1, NC, 1, F1)
+        dh1 = ops.fc_dgrad(dl, _w2d(wf2))
         du1, _, _ = ops.bn_act_bwd(dh1, False, u1, ones, zeros, zeros, ones, None, B, F1, hs, False)
         dwf1, dbf1 = ops.wgrad_simt(feat, du1, Cmid, F1, want_bias=True)
-        dfeat = ops.gemm_simt(du1, _w2d(wf1), Cmid, F1, 1, Cmid)           # [B][Cmid] fp32
-        dfeat.mul_(1.0 / R)                                                # gradient of the mean
+        dfeat = ops.fc_dgrad(du1, _w2d(wf1), 1.0 / R)                      # [B][Cmid] fp32, gradient of the mean
         dz, dgamma, dbeta = ops.bn_act_bwd(dfeat, True, z, scale, shift, mean, invstd, None, B, Cmid, hs,
                                            ctx.training)
         dse = (None, None, None, None)
@@ -365,10 +364,10 @@ class MoViNetTailFn(torch.autograd.Function):
                                  hs, 0.0, mask3d)
         feat = ops.pool_fwd(a, B, Cmid)
         F1, NC = wf1.shape[0], wf2.shape[0]
-        u1 = ops.gemm_simt(feat, wf1.detach(), F1, Cmid, Cmid, 1, bias=bf1.detach())
+        u1 = ops.fc_fwd(feat, wf1.detach(), bf1.detach())
         h1, bn1_state = bn_forward(u1, B, F1, gamma1.detach(), beta1.detach(), rmean1, rvar1, nbt1, training, eps,
                                    momentum, hs, 0.0, mask1d)
-        logits = ops.gemm_simt(h1, wf2.detach(), NC, F1, F1, 1, bias=bf2.detach())
+        logits = ops.fc_fwd(h1, wf2.detach(), bf2.detach())
         ctx.cache, ctx.training = cache, training
         ctx.shapes = (B, T, H, W, Cin, Cmid, R, F1, NC)
         ctx.save_for_backward(x5, z, mask3d, mask1d, *bn_state, feat, u1, *bn1_state, h1, wc, wf1, wf2)
@@ -383,12 +382,11 @@ class MoViNetTailFn(torch.autograd.Function):
         hs = ACT_CODES["hswish"]
         dl = dlogits.contiguous().float()
         dwf2, dbf2 = ops.wgrad_simt(h1, dl, F1, NC, want_bias=True)
-        dh1 = ops.gemm_simt(dl, wf2.detach(), F1, NC, 1, F1)
+        dh1 = ops.fc_dgrad(dl, wf2.detach())
         du1, dgamma1, dbeta1 = ops.bn_act_bwd(dh1, False, u1, scale1, shift1, mean1, invstd1, mask1d, B, F1, hs,
                                               ctx.training)
         dwf1, dbf1 = ops.wgrad_simt(feat, du1, Cmid, F1, want_bias=True)
-        dfeat = ops.gemm_simt(du1, wf1.detach(), Cmid, F1, 1, Cmid)
-        dfeat.mul_(1.0 / R)
+        dfeat = ops.fc_dgrad(du1, wf1.detach(), 1.0 / R)
         dz, dgamma, dbeta = ops.bn_act_bwd(dfeat, True, z, scale, shift, mean, invstd, mask3d, B, Cmid, hs,
                                            ctx.training)
         dwc, _ = pw_wgrad(x5.view(-1, Cin), dz, wc)

@@ -153,11 +153,54 @@ __global__ void se_fc_bwd_param_kernel(const float* __restrict__ a2, const float
 
 using namespace pb;
 
+// shared-memory staging of FC_BT input vectors (+ the k-slice reduction scratch): allow up to 96 KB
+constexpr int FC_MAX_K = 2560;
+static int fc_smem_attrs() {
+    static cudaError_t err = [] {
+        const int bytes = 96 * 1024;
+        cudaError_t e = cudaFuncSetAttribute(fc_rows_kernel<PB_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fc_rows_kernel<PB_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fc_rows_kernel<PB_ACT_HSIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fc_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        return e;
+    }();
+    return err == cudaSuccess ? PB_OK : cuda_fail(err, "cudaFuncSetAttribute(fc kernels)");
+}
+
+// Classifier-head linear layers (mobilenet.py:184-190, movinet.py:146-154): B = clips per call (64), so the
+// work is reading the weight matrix once; same kernels as the squeeze-excite layers.
+extern "C" int pb_fc_fwd(const float* X, const float* W, const float* bias, float* Y, int B, int N, int K,
+                         pb_stream_t stream) {
+    PB_REQUIRE(X && W && Y && B > 0 && N > 0 && K > 0, "fc_fwd: bad args");
+    PB_REQUIRE(K <= FC_MAX_K, "fc_fwd: K=%d too large for the shared-memory staging", K);
+    if (int e = fc_smem_attrs()) return e;
+    dim3 g(ceil_div(N, 32), ceil_div(B, FC_BT));
+    (void)launch_pdl(fc_rows_kernel<PB_ACT_NONE>, g, dim3(256), sizeof(float) * FC_BT * K, (cudaStream_t)stream, X, W, bias,
+                     Y, B, N, K);
+    PB_CHECK_LAUNCH("fc_fwd");
+    return PB_OK;
+}
+
+extern "C" int pb_fc_dgrad(const float* dY, const float* W, float* dX, int B, int N, int K, float scale,
+                           pb_stream_t stream) {
+    PB_REQUIRE(dY && W && dX && B > 0 && N > 0 && K > 0, "fc_dgrad: bad args");
+    PB_REQUIRE(N <= FC_MAX_K - 8 * 33, "fc_dgrad: N=%d too large for the shared-memory staging", N);
+    if (int e = fc_smem_attrs()) return e;
+    // dX[b][k] = scale * sum_n dY[b][n] W[n][k]: W [N][K] is the "Wt" of fc_cols with (K', N') = (N, K)
+    dim3 g(ceil_div(K, 32), ceil_div(B, FC_BT));
+    const size_t red_bytes = sizeof(float) * 8 * FC_BT * 33;
+    (void)launch_pdl(fc_cols_kernel, g, dim3(256), sizeof(float) * FC_BT * N + red_bytes, (cudaStream_t)stream, dY, W,
+                     (const float*)nullptr, dX, B, K, N, scale);
+    PB_CHECK_LAUNCH("fc_dgrad");
+    return PB_OK;
+}
+
 extern "C" int pb_se_fc_fwd(const float* mean, const float* W1, const float* b1, const float* W2, const float* b2,
                             float* hidden, float* gate, int B, int C, int Ch, pb_stream_t stream) {
     PB_REQUIRE(mean && W1 && b1 && W2 && b2 && hidden && gate && B > 0 && C > 0 && Ch > 0, "se_fc_fwd: bad args");
     cudaStream_t st = (cudaStream_t)stream;
-    PB_REQUIRE(C <= 1536 && Ch <= 1536, "se_fc_fwd: channel count too large for the shared-memory staging");
+    PB_REQUIRE(C <= FC_MAX_K && Ch <= FC_MAX_K, "se_fc_fwd: channel count too large for the shared-memory staging");
+    if (int e = fc_smem_attrs()) return e;
     dim3 g1(ceil_div(Ch, 32), ceil_div(B, FC_BT));
     (void)launch_pdl(fc_rows_kernel<PB_ACT_RELU>, dim3(g1), dim3(256), sizeof(float) * FC_BT * C, st, mean, W1, b1, hidden, B, Ch, C);
     PB_CHECK_LAUNCH("se_fc_fwd(1)");
@@ -182,7 +225,9 @@ extern "C" int pb_se_fc_bwd(const float* dgate, const float* mean, const float* 
     PB_CHECK_LAUNCH("se_fc_bwd(hsig)");
     // da1[b][j] = relu'(hidden) * sum_c da2[b][c] * W2[c][j]   (W2 is [C][Ch] = "Wt" with K=C, N=Ch)
     dim3 g1(ceil_div(Ch, 32), ceil_div(B, FC_BT));
-    PB_REQUIRE(C <= 1200 && Ch <= 1200, "se_fc_bwd: channel count too large for the shared-memory staging");
+    PB_REQUIRE(C <= FC_MAX_K - 8 * 33 && Ch <= FC_MAX_K - 8 * 33,
+               "se_fc_bwd: channel count too large for the shared-memory staging");
+    if (int e = fc_smem_attrs()) return e;
     const size_t red_bytes = sizeof(float) * 8 * FC_BT * 33;
     (void)launch_pdl(fc_cols_kernel, dim3(g1), dim3(256), sizeof(float) * FC_BT * C + red_bytes, st, a2, W2, hidden, a1, B, Ch, C, 1.f);
     PB_CHECK_LAUNCH("se_fc_bwd(da1)");

@@ -261,6 +261,29 @@ def pool_fwd(x: torch.Tensor, B: int, C: int) -> torch.Tensor:
     return mean
 
 
+def fc_fwd(X: torch.Tensor, W: torch.Tensor, bias=None) -> torch.Tensor:
+    """nn.Linear forward for a small batch: fp32 X [B][K], W [N][K] -> [B][N]."""
+    _chk(X, "fc_fwd.X"); _chk(W, "fc_fwd.W")
+    assert X.dtype == torch.float32 and W.dtype == torch.float32
+    B, K = X.shape
+    N = W.shape[0]
+    Y = torch.empty((B, N), dtype=torch.float32, device=X.device)
+    call("pb_fc_fwd", X.data_ptr(), W.data_ptr(), _p(bias), Y.data_ptr(), B, N, K, _st(), nbytes=(N * K + B * (N + K)) * 4)
+    return Y
+
+
+def fc_dgrad(dY: torch.Tensor, W: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """dX [B][K] = scale * dY [B][N] x W [N][K]  (fp32)."""
+    _chk(dY, "fc_dgrad.dY"); _chk(W, "fc_dgrad.W")
+    assert dY.dtype == torch.float32 and W.dtype == torch.float32
+    B, N = dY.shape
+    K = W.shape[1]
+    dX = torch.empty((B, K), dtype=torch.float32, device=dY.device)
+    call("pb_fc_dgrad", dY.data_ptr(), W.data_ptr(), dX.data_ptr(), B, N, K, float(scale), _st(),
+         nbytes=(N * K + B * (N + K)) * 4)
+    return dX
+
+
 def se_fc_fwd(mean, W1, b1, W2, b2) -> Tuple[torch.Tensor, torch.Tensor]:
     B, C = mean.shape
     Ch = W1.shape[0]

@@ -261,3 +261,22 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         ops.colstats(torch.zeros(4, 8), 8)                    # CPU tensor
     assert _lib.lib().pb_device_check() == 0
+
+
+@pytest.mark.parametrize("case", [(64, 1280, 960), (64, 2, 1280), (5, 100, 72), (64, 2048, 640), (1, 8, 2560), (9, 33, 8)])
+def test_fc_fwd_dgrad(case):
+    """Classifier-head nn.Linear layers (mobilenet.py:184-190, movinet.py:146-154): fp32, B <= a few dozen."""
+    from picklebot_b200 import ops
+    B, N, K = case
+    X, W, b = rnd(B, K, seed=1), rnd(N, K, seed=2, scale=0.1), rnd(N, seed=3)
+    assert rel_err(ops.fc_fwd(X, W, b), X @ W.t() + b) < 1e-5
+    assert rel_err(ops.fc_fwd(X, W), X @ W.t()) < 1e-5
+    if N <= 2560 - 8 * 33:
+        dY = rnd(B, N, seed=4)
+        assert rel_err(ops.fc_dgrad(dY, W, 0.25), 0.25 * (dY @ W)) < 1e-5
+
+
+def test_fc_rejects_oversize():
+    from picklebot_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.fc_fwd(rnd(2, 4096), rnd(8, 4096))
