@@ -88,8 +88,12 @@ int pb_stream_dwconv3d_fwd(const void* x, const void* stream_buf, const float* w
 int pb_pw_gemm_simt(const void* A, const float* W, long long w_sn, long long w_sk, const float* bias,
                     const float* ascale, const float* colscale, const float* coladd, void* C, int dtype,
                     int Bt, long long R, int K, int N, pb_stream_t stream);
+/* stats (optional, NULL to skip; needs N <= 256 and no epilogue vectors): BatchNorm sums of the stored (rounded)
+ * outputs, accumulated by the epilogue so that the following BatchNorm needs no statistics pass:
+ * stats[r][0][c] = partial sum, stats[r][1][c] = partial sum of squares over PB_STAT_REPLICAS copies r,
+ * c = column % stat_mod (stat_mod = real channel count of a row-folded problem, else N).  Zeroed here. */
 int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const float* bias,
-                  const float* colscale, const float* coladd, void* C,
+                  const float* colscale, const float* coladd, void* C, double* stats, int stat_mod,
                   int Bt, long long R, int K, int N, pb_stream_t stream);
 /* Weight gradient  dW[n][k] = sum_b ascale[b][k] * sum_r dC[b][r][n] * A[b][r][k]  (fp32, overwritten).
  * Optionally also dbias[n] = sum dC (NULL to skip). */

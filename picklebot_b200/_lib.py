@@ -27,7 +27,7 @@ SIGNATURES = {
     "pb_dwconv3d_wgrad": _DW,
     "pb_stream_dwconv3d_fwd": "pppppi" + "i" * 14 + "p",
     "pb_pw_gemm_simt": "ppllpppppiiliip",
-    "pb_pw_gemm_tc": "ppipppp" + "iliip",
+    "pb_pw_gemm_tc": "ppipppp" + "pi" + "iliip",
     "pb_pw_wgrad_simt": "pppppiiliip",
     "pb_pw_wgrad_tc": "pppppppiliip",
     "pb_cast_matrix": "ppiiiip",

@@ -103,22 +103,33 @@ def _row_fold(rows: int, K: int) -> int:
     return F
 
 
-def pw_fwd(A: torch.Tensor, w: torch.Tensor, cache: WeightCache, key: str, bias=None, gate=None, Bt: int = 1
-           ) -> torch.Tensor:
-    """[rows][K] x W[N][K]^T (+bias); gate [Bt][K] scales A's columns per sample (squeeze-excite)."""
+def pw_fwd(A: torch.Tensor, w: torch.Tensor, cache: WeightCache, key: str, bias=None, gate=None, Bt: int = 1,
+           want_stats: bool = False, fuse_stats: bool = True):
+    """[rows][K] x W[N][K]^T (+bias); gate [Bt][K] scales A's columns per sample (squeeze-excite).
+    want_stats: returns (C, sums) where sums are the BatchNorm column sums of C if the tensor-core epilogue could
+    accumulate them (else None and the caller runs the statistics pass)."""
     W = _w2d(w)
     N, K = W.shape
+    C = sums = None
     if ops.use_tc(A.dtype, K, N):
+        fuse = want_stats and fuse_stats and bias is None and N <= 256
         if gate is not None:
             Wb = ops.fold_gate(W, gate)
-            return gemm_tc.gemm(A, Wb, N, K, Bw=Bt, Bt=Bt, bias=bias)
-        Wb = cache.get((key, "bf16"), w, lambda: ops.cast_matrix(W, N, K, torch.bfloat16))
-        F = _row_fold(A.numel() // K, K) if bias is None else 1
-        if F > 1:
-            Wf = cache.get((key, "bf16", F), w, lambda: ops.block_diag(Wb, F))
-            return gemm_tc.gemm(A, Wf, N * F, K * F).view(-1, N)
-        return gemm_tc.gemm(A, Wb, N, K, Bw=1, Bt=1, bias=bias)
-    return ops.gemm_simt(A, W, N, K, K, 1, bias=bias, ascale=gate, Bt=Bt)
+            C = gemm_tc.gemm(A, Wb, N, K, Bw=Bt, Bt=Bt, bias=bias, stat_mod=N if fuse else 0)
+        else:
+            Wb = cache.get((key, "bf16"), w, lambda: ops.cast_matrix(W, N, K, torch.bfloat16))
+            F = _row_fold(A.numel() // K, K) if bias is None else 1
+            if F > 1 and (not fuse or N * F <= 256):
+                Wf = cache.get((key, "bf16", F), w, lambda: ops.block_diag(Wb, F))
+                C = gemm_tc.gemm(A, Wf, N * F, K * F, stat_mod=N if fuse else 0)
+            else:
+                C = gemm_tc.gemm(A, Wb, N, K, Bw=1, Bt=1, bias=bias, stat_mod=N if fuse else 0)
+        if fuse:
+            C, sums = C
+        C = C.view(-1, N)
+    else:
+        C = ops.gemm_simt(A, W, N, K, K, 1, bias=bias, ascale=gate, Bt=Bt)
+    return (C, sums) if want_stats else C
 
 
 def pw_dgrad(dC: torch.Tensor, w: torch.Tensor, cache: WeightCache, key: str) -> torch.Tensor:
@@ -174,11 +185,15 @@ def se_pw2_backward(dz: torch.Tensor, y2: torch.Tensor, w2: torch.Tensor, cache:
 # BatchNorm(+act+dropout) helper shared by every block
 # ---------------------------------------------------------------------------------------------
 def bn_forward(z: torch.Tensor, B: int, C: int, gamma, beta, rmean, rvar, nbt, training: bool, eps: float,
-               momentum: float, act: int, slope: float, mask):
-    """z: NDHWC/2-D activations with C channels.  Returns (out, (scale, shift, mean, invstd))."""
+               momentum: float, act: int, slope: float, mask, sums=None):
+    """z: NDHWC/2-D activations with C channels.  Returns (out, (scale, shift, mean, invstd)).
+    sums: batch statistics already accumulated by the producing GEMM's epilogue (else a pass over z)."""
     M = z.numel() // C
     use_batch = training or rmean is None
-    sums = ops.colstats(z, C) if use_batch else None
+    if not use_batch:
+        sums = None
+    elif sums is None:
+        sums = ops.colstats(z, C)
     scale, shift, mean, invstd = ops.bn_finalize(sums, M, gamma, beta, rmean, rvar, use_batch, momentum, eps, C,
                                                  z.device)
     if use_batch and nbt is not None:
@@ -207,9 +222,10 @@ class BottleneckFn(torch.autograd.Function):
         if cfg.use_se:
             pooled = ops.pool_fwd(y2, B, Cexp)
             hidden, gate = ops.se_fc_fwd(pooled, _w2d(se_w1), se_b1.detach(), _w2d(se_w2), se_b2.detach())
-        z = pw_fwd(y2.view(-1, Cexp), w2, cache, "w2", gate=gate, Bt=B if gate is not None else 1)
+        z, zsums = pw_fwd(y2.view(-1, Cexp), w2, cache, "w2", gate=gate, Bt=B if gate is not None else 1,
+                          want_stats=True, fuse_stats=training or rmean is None)
         out, bn_state = bn_forward(z, B, Cout, gamma.detach(), beta.detach(), rmean, rvar, nbt, training, cfg.eps,
-                                   cfg.momentum, cfg.act, cfg.slope, mask)
+                                   cfg.momentum, cfg.act, cfg.slope, mask, sums=zsums)
         ctx.cfg, ctx.cache, ctx.training = cfg, cache, training
         ctx.shapes = (B, T, H, W, Cin, Cexp, Cout, To, Ho, Wo)
         ctx.save_for_backward(x5, y1, y2, z, mask, pooled, hidden, gate, *bn_state,

@@ -54,6 +54,8 @@ struct GemmParams {
     const float* colscale;
     const float* coladd;
     __nv_bfloat16* C;
+    double* stats;     // optional BatchNorm statistics of C: [PB_STAT_REPLICAS][2][stat_mod] sums of x and x^2
+    int stat_mod;      // real channel count (column c of a row-folded problem is channel c % stat_mod)
 };
 
 __device__ __forceinline__ void ldg16(const float* p, float (&v)[16]) {
@@ -64,7 +66,7 @@ __device__ __forceinline__ void ldg16(const float* p, float (&v)[16]) {
     }
 }
 
-template <bool EPI>      // EPI: any of bias / colscale / coladd present
+template <bool EPI, bool STATS>   // EPI: any of bias / colscale / coladd present; STATS: column sums of C
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -149,6 +151,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;
         const int group = (warp - 4) >> 2;
         uint8_t* stage_w = tiles + (size_t)p.stages * stage_bytes + (size_t)(warp - 4) * EPI_STAGE_BYTES;
+        // STATS: after the staging transpose a lane owns 8 fixed columns of each 64-column panel, so the
+        // BatchNorm sums of the rounded outputs accumulate in registers over every tile of this CTA
+        float st_sum[STATS ? 4 : 1][8], st_sq[STATS ? 4 : 1][8];
+#pragma unroll
+        for (int pi = 0; pi < (STATS ? 4 : 1); ++pi)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { st_sum[pi][i] = 0.f; st_sq[pi][i] = 0.f; }
         long long it = 0;
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int a = (int)(it & 1);
@@ -205,6 +214,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                         __syncwarp();
+                    }
+                    continue;
+                }
+                if (STATS) {
+#pragma unroll
+                    for (int pi = 0; pi < 4; ++pi) {
+                        const int c0 = pi * 64;
+                        if (c0 < p.block_n) {
+                            const int pw = min(64, p.block_n - c0);                                 // 16, 32, 48 or 64
+                            uint32_t r[4][16];
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                if (g * 16 < pw) tmem_ld16(taddr + (uint32_t)(c0 + g * 16), r[g]);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int n0 = n_base + c0 + g * 16;
+                                if (g * 16 < pw && n0 < p.N) {
+                                    float v[16];
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[g][j]);
+                                    uint4 o0, o1;
+                                    o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+                                    o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+                                    o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+                                    o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+                                    uint8_t* rowp = stage_w + lane * 128;
+                                    *reinterpret_cast<uint4*>(rowp + (((2 * g) ^ (lane & 7)) << 4)) = o0;
+                                    *reinterpret_cast<uint4*>(rowp + (((2 * g + 1) ^ (lane & 7)) << 4)) = o1;
+                                }
+                            }
+                            __syncwarp();
+                            // fixed column slot per lane: cprs lanes per row (2, 4 or 8), pw/8 of them active
+                            const int sh = pw == 16 ? 1 : pw == 32 ? 2 : 3;
+                            const int ch = lane & ((1 << sh) - 1), rstep = 32 >> sh;
+                            const int col = n_base + c0 + ch * 8;
+                            if (ch * 8 < pw && col < p.N) {
+                                for (int rr = lane >> sh; rr < rows_ok; rr += rstep) {
+                                    const uint4 v4 = *reinterpret_cast<const uint4*>(stage_w + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                                    *reinterpret_cast<uint4*>(cbase + (long long)rr * p.N + col) = v4;
+                                    const uint32_t u[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const float lo = bf16_lo(u[i]), hi = bf16_hi(u[i]);
+                                        st_sum[pi][2 * i] += lo;     st_sq[pi][2 * i] = fmaf(lo, lo, st_sq[pi][2 * i]);
+                                        st_sum[pi][2 * i + 1] += hi; st_sq[pi][2 * i + 1] = fmaf(hi, hi, st_sq[pi][2 * i + 1]);
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                        }
                     }
                     continue;
                 }
@@ -269,6 +329,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             mbar_arrive(&tempty_bar[a]);
         }
+        if (STATS) {
+            double* dst = p.stats + (size_t)(blockIdx.x % PB_STAT_REPLICAS) * 2 * p.stat_mod;
+#pragma unroll
+            for (int pi = 0; pi < 4; ++pi) {
+                const int c0 = pi * 64;
+                if (c0 < p.block_n) {
+                    const int pw = min(64, p.block_n - c0);
+                    const int sh = pw == 16 ? 1 : pw == 32 ? 2 : 3;
+                    const int ch = lane & ((1 << sh) - 1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float a0 = st_sum[pi][i], a1 = st_sq[pi][i];
+                        for (int off = 16; off >= (1 << sh); off >>= 1) {     // lanes that share the column slot
+                            a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+                            a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+                        }
+                        const int col = c0 + ch * 8 + i;
+                        if (lane < (1 << sh) && ch * 8 < pw && col < p.N) {
+                            atomicAdd(&dst[col % p.stat_mod], (double)a0);
+                            atomicAdd(&dst[p.stat_mod + col % p.stat_mod], (double)a1);
+                        }
+                    }
+                }
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -285,7 +370,8 @@ using namespace pb;
 using namespace pb::tc;
 
 extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const float* bias, const float* colscale,
-                             const float* coladd, void* C, int Bt, long long R, int K, int N, pb_stream_t stream) {
+                             const float* coladd, void* C, double* stats, int stat_mod, int Bt, long long R, int K,
+                             int N, pb_stream_t stream) {
     PB_REQUIRE(A && W_bf16 && C, "pw_gemm_tc: null pointer");
     PB_REQUIRE(Bt > 0 && R > 0 && K > 0 && N > 0, "pw_gemm_tc: empty problem");
     PB_REQUIRE(K % 8 == 0 && N % 8 == 0, "pw_gemm_tc: K=%d and N=%d must be multiples of 8", K, N);
@@ -316,6 +402,12 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     p.stages = std::min(MAX_STAGES, RING_BYTES / stage_bytes);
     PB_REQUIRE(p.stages >= 2, "pw_gemm_tc: internal tiling error");
     p.bias = bias; p.colscale = colscale; p.coladd = coladd; p.C = (__nv_bfloat16*)C;
+    p.stats = stats; p.stat_mod = stat_mod;
+    if (stats) {
+        PB_REQUIRE(!bias && !colscale && !coladd && p.n_tiles == 1, "pw_gemm_tc: fused statistics need N <= 256 and no epilogue vectors");
+        PB_REQUIRE(stat_mod > 0 && N % stat_mod == 0, "pw_gemm_tc: stat_mod=%d must divide N=%d", stat_mod, N);
+        PB_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * PB_STAT_REPLICAS * 2 * stat_mod, (cudaStream_t)stream));
+    }
     const size_t smem = (size_t)p.stages * stage_bytes + 8 * EPI_STAGE_BYTES + 1024;
 
     CUtensorMap tmA, tmW;
@@ -334,9 +426,11 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        attr_err = cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+            attr_err = cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(gemm_tc_kernel)");
     int dev = 0, sms = 148;
@@ -344,9 +438,11 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = (int)std::min<long long>(p.total_tiles, sms);
     if (bias || colscale || coladd)
-        PB_CUDA(launch_pdl(gemm_tc_kernel<true>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
+        PB_CUDA(launch_pdl(gemm_tc_kernel<true, false>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
+    else if (stats)
+        PB_CUDA(launch_pdl(gemm_tc_kernel<false, true>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
     else
-        PB_CUDA(launch_pdl(gemm_tc_kernel<false>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
+        PB_CUDA(launch_pdl(gemm_tc_kernel<false, false>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
     PB_CHECK_LAUNCH("gemm_tc_kernel");
     return PB_OK;
 }

@@ -15,17 +15,20 @@ _WGRAD_READY = os.environ.get("PB_TC_WGRAD", "1") != "0"
 
 
 def gemm(A: torch.Tensor, Wb: torch.Tensor, N: int, K: int, Bw: int = 1, Bt: int = 1, bias=None, colscale=None,
-         coladd=None) -> torch.Tensor:
+         coladd=None, stat_mod: int = 0):
     """A bf16 [Bt][R][K] (contiguous), Wb bf16 [Bw][N][K] -> bf16 [Bt*R][N];
-    C = (A W^T + bias) * colscale[b] + coladd[b]."""
+    C = (A W^T + bias) * colscale[b] + coladd[b].
+    stat_mod > 0: also returns the BatchNorm sums of C ([STAT_REPLICAS][2][stat_mod] fp64, channel = column % stat_mod),
+    accumulated by the GEMM epilogue (N <= 256, no epilogue vectors)."""
     _chk(A, "gemm_tc.A"); _chk(Wb, "gemm_tc.W")
     assert A.dtype == torch.bfloat16 and Wb.dtype == torch.bfloat16
     rows = A.numel() // K
     R = rows // Bt
     C = torch.empty((rows, N), dtype=torch.bfloat16, device=A.device)
+    sums = torch.empty((_lib.STAT_REPLICAS, 2, stat_mod), dtype=torch.float64, device=A.device) if stat_mod else None
     call("pb_pw_gemm_tc", A.data_ptr(), Wb.data_ptr(), Bw, _p(bias), _p(colscale), _p(coladd), C.data_ptr(),
-         Bt, R, K, N, _st(), nbytes=(A.numel() + C.numel() + Wb.numel()) * 2)
-    return C
+         _p(sums), stat_mod, Bt, R, K, N, _st(), nbytes=(A.numel() + C.numel() + Wb.numel()) * 2)
+    return (C, sums) if stat_mod else C
 
 
 def wgrad_ready() -> bool:

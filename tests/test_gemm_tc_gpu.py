@@ -63,6 +63,27 @@ def test_gemm_tc_row_folded(case):
     assert rel_err(C.float(), A.float() @ W.float().t()) < 6e-3
 
 
+@pytest.mark.parametrize("case", [(1, 5000, 16, 16, 4), (1, 3001, 64, 24, 1), (2, 931, 960, 160, 1), (1, 4444, 72, 40, 1),
+                                  (3, 777, 480, 112, 1), (1, 2000, 240, 80, 1), (1, 9000, 16, 64, 4), (64, 49, 576, 96, 1),
+                                  (1, 1000, 144, 256, 1), (1, 130, 8, 8, 1)])
+def test_gemm_tc_fused_bn_statistics(case):
+    """pb_pw_gemm_tc(stats=...): the epilogue's column sums equal a statistics pass over the stored outputs."""
+    from picklebot_b200 import gemm_tc, ops
+    Bt, R, K, N, F = case
+    A = rnd(Bt * R, K, seed=1).bfloat16()
+    W = rnd(N, K, seed=2, scale=0.3).bfloat16()
+    if F > 1:
+        C, sums = gemm_tc.gemm(A, ops.block_diag(W, F), N * F, K * F, stat_mod=N)
+        C = C.view(-1, N)
+    else:
+        C, sums = gemm_tc.gemm(A, W, N, K, Bw=1, Bt=Bt, stat_mod=N)
+    assert rel_err(C.float(), A.float() @ W.float().t()) < 6e-3
+    got = sums.sum(0)
+    ref = torch.stack([C.double().sum(0), (C.double() ** 2).sum(0)])
+    assert (got - ref).abs().max() / ref.abs().max() < 1e-5
+    assert rel_err(got[1].float(), ref[1].float()) < 1e-5
+
+
 def test_gemm_tc_matches_simt_bitwise_scale():
     """Same operands through the CUDA-core kernel: both accumulate in fp32, so they agree to bf16 round-off."""
     from picklebot_b200 import gemm_tc, ops

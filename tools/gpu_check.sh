@@ -1,7 +1,7 @@
 # GPU regression + bench in one gpurun call: kernel and model parity tests, then the default bench with the
 # per-kernel table.  usage: bash tools/gpu_check.sh [pytest-args]
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --tb=short "$@" 2>&1 | tail -3
+timeout 900 python -m pytest tests -m gpu -q --tb=short "$@" 2>&1 | tail -3 | tee gpurun_out/pytest_tail.txt
 PB_BENCH_DETAIL=gpurun_out/detail.txt timeout 400 python bench.py --steps 4 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 python - <<'PY'
 import json; d=json.load(open("gpurun_out/bench.json")); print(d["value"], d["ms_per_step"], d["e2e"]["value"])
