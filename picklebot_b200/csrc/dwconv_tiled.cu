@@ -8,14 +8,20 @@
 // nothing and needs no bounds checks, and the frames created by the reference's scalar temporal padding
 // (mobilenet.py:67-75) are written as zeros without reading anything.  Each consumer thread owns 4 channels
 // (8-byte vectors) and a strip of output pixels: every staged vector is unpacked once and fed to all the
-// outputs of the strip that use it with packed fp32 FMAs (fma.rn.f32x2); filter taps stay in registers.
+// outputs of the strip that use it with packed fp32 FMAs (fma.rn.f32x2); 3x3 taps stay in registers, 5x5 taps
+// are staged per CTA in shared memory (they spilled otherwise).
+//
+// A tcgen05 formulation was built and measured (depthwise = GEMM against diag(w_tap), the im2col operand of
+// tap (i,j) being the same swizzled halo tile read from a start address shifted by i*Wi+j rows; git history:
+// "Depthwise 5x5 stride-1 forward/dgrad on tcgen05").  It is correct, but every tap re-reads the whole tile
+// from shared memory (25 passes at 128 B/clk), which bounds it near 2.5 TB/s x the fraction of useful MMA rows:
+// 1.8 TB/s on 28x28 planes against 2.1-2.3 TB/s for the kernels below, so it was dropped.
 //
 //   forward            : y  = conv(x, w)                     (also the stride-1 input gradient: flipped w)
 //   input gradient, s=2: dx = gather of dy over the taps whose parity matches
 //   weight gradient    : dw accumulated in registers over all tiles of the CTA, reduced once at the end
 //                        (shared-memory sums, then one fp32 atomic per tap and channel per CTA)
 #include <algorithm>
-#include <cstdlib>
 #include <mutex>
 
 #include "dwconv.cuh"
@@ -59,6 +65,12 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 // shared bookkeeping of the tile pipeline
 struct TileCtx {
     uint64_t full[DWT_MAX_STAGES];
@@ -96,6 +108,18 @@ __device__ __forceinline__ void pipeline_init(TileCtx& cx, const DwTile& p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&cx.full[s], 1); mbar_init(&cx.empty[s], DWT_CONSUMERS / 32); }
         fence_barrier_init();
+    }
+    __syncthreads();
+}
+
+// 5x5 filters: taps of this CTA's channel block as fp32 [tap][Cb] in shared memory (all threads, before the
+// role split); `flip` reverses the tap order (stride-1 input gradient).
+template <int K>
+__device__ __forceinline__ void stage_taps(float* wsm, const float* __restrict__ w_tc, const DwTile& p, int c_base, int flip) {
+    for (int e = threadIdx.x; e < K * K * p.Cb; e += DWT_THREADS) {
+        const int tap = e / p.Cb, c = e - tap * p.Cb;
+        const int src = flip ? K * K - 1 - tap : tap;
+        wsm[e] = (c_base + c < p.C) ? w_tc[(long long)src * p.C + c_base + c] : 0.f;
     }
     __syncthreads();
 }
@@ -145,6 +169,7 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
     pdl_trigger();
     pipeline_init(cx, p);
     pdl_wait();                 // barrier setup above overlaps the previous kernel's tail
+    if constexpr (K == 5) stage_taps<K>(reinterpret_cast<float*>(ring + (size_t)p.stages * p.stage_bytes), w_tc, p, c_base, p.flip);
     const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid >= DWT_CONSUMERS) {
@@ -162,25 +187,27 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
     const int g = tid % p.Gb;
     const bool active = tid < ppp * p.Gb && (c_base + g * 4) < p.C;
     const int slot = tid / p.Gb;
-    // K == 3: fp32 pairs (36 registers); K == 5: packed bf16 pairs (50 registers; lossless, the tap-major
-    // weights were rounded to bf16 for this dtype already)
-    constexpr bool PACKED = (K == 5);
-    float2 wv[PACKED ? 1 : K * K][2];
-    uint32_t wp[PACKED ? K * K : 1][2];
+    // K == 3: taps in registers as fp32 pairs (36 registers).  K == 5: 100 fp32 (or 50 packed) registers do not
+    // fit next to the window and the accumulators under the 128-register cap of 2 CTAs/SM (they spilled), so the
+    // taps are staged once per CTA as fp32 [tap][Cb] in shared memory and fetched with one LDS.128 per use.
+    constexpr bool SMEMW = (K == 5);
+    float2 wv[SMEMW ? 1 : K * K][2];
+    if constexpr (!SMEMW) {
 #pragma unroll
-    for (int t = 0; t < K * K; ++t) {
-        const int src = p.flip ? (K * K - 1 - t) : t;
+        for (int t = 0; t < K * K; ++t) {
+            const int src = p.flip ? (K * K - 1 - t) : t;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            float lo = 0.f, hi = 0.f;
-            if (active) {
-                const float* wsrc = w_tc + (long long)src * p.C + c_base + g * 4 + c * 2;
-                lo = wsrc[0]; hi = wsrc[1];
+            for (int c = 0; c < 2; ++c) {
+                float lo = 0.f, hi = 0.f;
+                if (active) {
+                    const float* wsrc = w_tc + (long long)src * p.C + c_base + g * 4 + c * 2;
+                    lo = wsrc[0]; hi = wsrc[1];
+                }
+                wv[t][c] = make_float2(lo, hi);
             }
-            if constexpr (PACKED) wp[t][c] = pack_bf16x2(lo, hi);
-            else wv[t][c] = make_float2(lo, hi);
         }
     }
+    const uint32_t wsm_g = smem_u32(ring + (size_t)p.stages * p.stage_bytes) + (uint32_t)(g * 16);
     const int nstrips = p.Wt / WS;
     const int items = p.Ht * nstrips;
     const uint32_t ring_u32 = smem_u32(ring);
@@ -206,7 +233,7 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
 #pragma unroll
                 for (int i = 0; i < K; ++i, rowa += row_bytes) {
                     uint32_t a = rowa;
-                    if constexpr (!PACKED) {
+                    if constexpr (!SMEMW) {
 #pragma unroll
                         for (int j = 0; j < (WS - 1) * S + K; ++j, a += cb_bytes) {
                             const uint2 u = lds64(a);
@@ -230,7 +257,8 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
                         }
 #pragma unroll
                         for (int t = 0; t < K; ++t) {
-                            const float2 w0 = unpack2(wp[i * K + t][0]), w1 = unpack2(wp[i * K + t][1]);
+                            const float4 w4 = lds128f(wsm_g + (uint32_t)((i * K + t) * p.Cb * 4));
+                            const float2 w0 = make_float2(w4.x, w4.y), w1 = make_float2(w4.z, w4.w);
 #pragma unroll
                             for (int o = 0; o < WS; ++o) {
                                 ffma2(acc[o][0], win[o * S + t][0], w0);
@@ -278,6 +306,7 @@ dw_dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmD, const float* __r
     pdl_trigger();
     pipeline_init(cx, p);
     pdl_wait();                 // barrier setup above overlaps the previous kernel's tail
+    if constexpr (K == 5) stage_taps<K>(reinterpret_cast<float*>(ring + (size_t)p.stages * p.stage_bytes), w_tc, p, c_base, 0);
     const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid >= DWT_CONSUMERS) {
@@ -295,18 +324,23 @@ dw_dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmD, const float* __r
     const int g = tid % p.Gb;
     const bool active = tid < ppp * p.Gb && (c_base + g * 4) < p.C;
     const int slot = tid / p.Gb;
-    uint32_t wp[K * K][2];                     // packed bf16 pairs
+    // K == 3: packed bf16 pairs in registers; K == 5: fp32 taps in shared memory (see dw_fwd_tma_kernel)
+    constexpr bool SMEMW = (K == 5);
+    uint32_t wp[SMEMW ? 1 : K * K][2];
+    if constexpr (!SMEMW) {
 #pragma unroll
-    for (int t = 0; t < K * K; ++t)
+        for (int t = 0; t < K * K; ++t)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            float lo = 0.f, hi = 0.f;
-            if (active) {
-                const float* wsrc = w_tc + (long long)t * p.C + c_base + g * 4 + c * 2;
-                lo = wsrc[0]; hi = wsrc[1];
+            for (int c = 0; c < 2; ++c) {
+                float lo = 0.f, hi = 0.f;
+                if (active) {
+                    const float* wsrc = w_tc + (long long)t * p.C + c_base + g * 4 + c * 2;
+                    lo = wsrc[0]; hi = wsrc[1];
+                }
+                wp[t][c] = pack_bf16x2(lo, hi);
             }
-            wp[t][c] = pack_bf16x2(lo, hi);
-        }
+    }
+    const uint32_t wsm_g = smem_u32(ring + (size_t)p.stages * p.stage_bytes) + (uint32_t)(g * 16);
     const int nstrips = p.Wt / XS;
     const int items = p.Ht * nstrips;
     const uint32_t ring_u32 = smem_u32(ring);
@@ -350,7 +384,13 @@ dw_dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmD, const float* __r
                             if (((o + P - j) & 1) == 0) {
                                 constexpr int dummy = 0; (void)dummy;
                                 const int cl = ((o + P - j) >> 1) + P / 2;
-                                const float2 w0 = unpack2(wp[i * K + j][0]), w1 = unpack2(wp[i * K + j][1]);
+                                float2 w0, w1;
+                                if constexpr (SMEMW) {
+                                    const float4 w4 = lds128f(wsm_g + (uint32_t)((i * K + j) * p.Cb * 4));
+                                    w0 = make_float2(w4.x, w4.y); w1 = make_float2(w4.z, w4.w);
+                                } else {
+                                    w0 = unpack2(wp[i * K + j][0]); w1 = unpack2(wp[i * K + j][1]);
+                                }
                                 ffma2(acc[o][0], win[cl][0], w0);
                                 ffma2(acc[o][1], win[cl][1], w1);
                             }
@@ -489,6 +529,7 @@ struct PlanIn {
     int K, S, WS;          // S: source step per destination pixel (1 or 2); dgrad-s2 passes S = 0 (half-rate)
     int pS;
     int with_dst_tile;     // wgrad: the dy tile is staged too
+    int reserve;           // shared memory kept for other uses (5x5 taps), bytes
 };
 
 static bool plan_tile(const PlanIn& in, DwTile& p) {
@@ -533,7 +574,7 @@ static bool plan_tile(const PlanIn& in, DwTile& p) {
     p.box_bytes = p.Hi * p.Wi * p.Cb * 2;
     p.box2_bytes = in.with_dst_tile ? p.Ht * p.Wt * p.Cb * 2 : 0;
     p.stage_bytes = (p.box_bytes + 127) / 128 * 128 + (p.box2_bytes + 127) / 128 * 128;
-    p.stages = std::min(DWT_MAX_STAGES, (108 * 1024) / p.stage_bytes);
+    p.stages = std::min(DWT_MAX_STAGES, (108 * 1024 - in.reserve) / p.stage_bytes);
     if (p.stages < 2) return false;
     p.flip = 0;
     return true;
@@ -588,7 +629,8 @@ template <int K, int S, int WS>
 static bool launch_fwd(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y, const DwDims& d, int pT, int sT,
                        int flip, cudaStream_t st) {
     DwTile p;
-    PlanIn in{d.B, d.C, d.To, d.Ho, d.Wo, K, S, WS, d.pH, 0};
+    constexpr int TAPS_BYTES = K == 5 ? K * K * 128 * 4 : 0;           // fp32 [tap][Cb <= 128]
+    PlanIn in{d.B, d.C, d.To, d.Ho, d.Wo, K, S, WS, d.pH, 0, TAPS_BYTES};
     if (!plan_tile(in, p)) return false;
     if (!plan_frames(p, d.To, d.T, sT, -pT, 1)) return false;      // source frame = to*sT - pT
     p.flip = flip;
@@ -596,7 +638,8 @@ static bool launch_fwd(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16*
     if (make_map5(&tm, x, d.C, d.W, d.H, d.T, d.B, p.Cb, p.Wi, p.Hi) != PB_OK) return false;
     static std::once_flag once;
     set_smem_once(dw_fwd_tma_kernel<K, S, WS>, once);
-    (void)launch_pdl(dw_fwd_tma_kernel<K, S, WS>, dim3(persistent_grid(p)), dim3(DWT_THREADS), (size_t)p.stages * p.stage_bytes + 128, st,
+    (void)launch_pdl(dw_fwd_tma_kernel<K, S, WS>, dim3(persistent_grid(p)), dim3(DWT_THREADS),
+                     (size_t)p.stages * p.stage_bytes + 128 + TAPS_BYTES, st,
                        tm, w_tc, y, p);   // errors: caller's PB_CHECK_LAUNCH
     return true;
 }
@@ -606,14 +649,16 @@ static bool launch_dgrad_s2(const __nv_bfloat16* dy, const float* w_tc, __nv_bfl
                             cudaStream_t st) {
     constexpr int XS = 4;
     DwTile p;
-    PlanIn in{d.B, d.C, d.T, d.H, d.W, K, 0, XS, d.pH, 0};
+    constexpr int TAPS_BYTES = K == 5 ? K * K * 128 * 4 : 0;
+    PlanIn in{d.B, d.C, d.T, d.H, d.W, K, 0, XS, d.pH, 0, TAPS_BYTES};
     if (!plan_tile(in, p)) return false;
     if (!plan_frames(p, d.T, d.To, 1, d.pT, d.sT)) return false;   // source frame = (t + pT)/sT
     CUtensorMap tm;
     if (make_map5(&tm, dy, d.C, d.Wo, d.Ho, d.To, d.B, p.Cb, p.Wi, p.Hi) != PB_OK) return false;
     static std::once_flag once;
     set_smem_once(dw_dgrad_s2_tma_kernel<K, XS>, once);
-    (void)launch_pdl(dw_dgrad_s2_tma_kernel<K, XS>, dim3(persistent_grid(p)), dim3(DWT_THREADS), (size_t)p.stages * p.stage_bytes + 128, st,
+    (void)launch_pdl(dw_dgrad_s2_tma_kernel<K, XS>, dim3(persistent_grid(p)), dim3(DWT_THREADS),
+                     (size_t)p.stages * p.stage_bytes + 128 + TAPS_BYTES, st,
                        tm, w_tc, dx, p);
     return true;
 }
@@ -622,7 +667,7 @@ template <int K, int S, int WS>
 static bool launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw_tc, const DwDims& d,
                          cudaStream_t st) {
     DwTile p;
-    PlanIn in{d.B, d.C, d.To, d.Ho, d.Wo, K, S, WS, d.pH, 1};
+    PlanIn in{d.B, d.C, d.To, d.Ho, d.Wo, K, S, WS, d.pH, 1, 0};
     if (!plan_tile(in, p)) return false;
     if (p.Gb * K > DWT_CONSUMERS) return false;
     if (K * K * p.Cb * 4 > p.stages * p.stage_bytes) return false;
@@ -635,254 +680,6 @@ static bool launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float*
     set_smem_once(dw_wgrad_tma_kernel<K, S, WS>, once);
     (void)launch_pdl(dw_wgrad_tma_kernel<K, S, WS>, dim3(persistent_grid(p)), dim3(DWT_THREADS), (size_t)p.stages * p.stage_bytes + 128, st,
                        tmx, tmd, dw_tc, p);
-    return true;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Stride-1 forward / input gradient on the tensor cores.
-//
-// A depthwise filter is a GEMM against a diagonal matrix: for a group of 16 channels and one tap (i, j)
-//     D[pixel][c] += A_tap[pixel][c'] * diag(w[tap][c'])[c'][c],      A_tap[pixel] = X[pixel + i*Wi + j].
-// The TMA halo tile [Hi][Wi][64 channels] sits in shared memory with one 128-byte (SWIZZLE_128B) row per
-// pixel, so A_tap is the SAME tile read from a start address shifted by (i*Wi + j) rows: the im2col costs
-// nothing, and "output pixel" simply enumerates the halo tile row-major (the few pixels that fall into the
-// halo columns are computed and dropped).  Per 128-pixel MMA tile and tap that is four M128 x N16 x K16
-// tcgen05.mma (one per 16-channel group; 15/16 of the multiplies hit zeros, but the tensor pipe has two
-// orders of magnitude to spare here), accumulators [128 pixels][64 channels] fp32 in TMEM.  The CUDA-core
-// path spends ~135 issue slots per output vector on a 5x5 filter and tops out at 1.2 TB/s; this one is bound
-// by the shared-memory operand reads of the MMAs (one pass over the tile per tap).  Used for 5x5 filters,
-// stride 1, C >= 96, when most MMA rows are real output pixels (see launch_fwd_tc).
-//
-// Warp roles (384 threads, one CTA per SM): warp 0 = TMA producer, warps 1-4 = MMA issuers (one per 16-channel
-// group), warp 5 = TMEM allocator, warps 8-11 = epilogue (TMEM -> bf16 -> per-warp swizzled staging rows -> 128-byte row stores).
-// ------------------------------------------------------------------------------------------------
-constexpr int DTC_CB = 64;                 // channels per CTA (one 128-byte swizzle row per pixel)
-constexpr int DTC_THREADS = 384;
-constexpr int DTC_MAX_MT = 4;              // 128-pixel MMA tiles per halo tile (2 x 4 x 64 TMEM columns)
-
-template <int K>
-__global__ void __launch_bounds__(DTC_THREADS, 1)
-dw_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w_tc,
-                 __nv_bfloat16* __restrict__ y, const DwTile p, const int m_tiles) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[DWT_MAX_STAGES], empty_bar[DWT_MAX_STAGES], tfull_bar[2], tempty_bar[2];
-    __shared__ uint32_t tmem_base_s;
-    pdl_trigger();
-    constexpr int KK = K * K;
-    constexpr int WDIAG_BYTES = KK * 4 * 512;          // [tap][16-channel group] 16x16 bf16 core-matrix tiles
-    const uint32_t raw = smem_u32(smem_raw);
-    uint8_t* ring = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    uint8_t* wdiag = ring + (size_t)p.stages * p.stage_bytes;
-    uint8_t* staging = wdiag + WDIAG_BYTES;             // 4 warps x 32 rows x 128 B
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int c_base = blockIdx.y * DTC_CB;
-
-    if (tid == 0) {
-        tma_prefetch_desc(&tmX);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 4); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 4); mbar_init(&tempty_bar[a], 128); }
-        fence_barrier_init();
-    }
-    if (warp == 5) tmem_alloc(&tmem_base_s, 512);
-    for (int e = tid; e < WDIAG_BYTES / 16; e += DTC_THREADS) reinterpret_cast<uint4*>(wdiag)[e] = make_uint4(0u, 0u, 0u, 0u);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-    pdl_wait();
-    // diagonal weight tiles, K-major no-swizzle core matrices: offset(n, k) = (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2
-    for (int e = tid; e < KK * DTC_CB; e += DTC_THREADS) {
-        const int tap = e / DTC_CB, c = e - tap * DTC_CB;
-        const int src = p.flip ? KK - 1 - tap : tap;
-        const float wv = (c_base + c < p.C) ? w_tc[(long long)src * p.C + c_base + c] : 0.f;
-        const int n = c & 15;
-        *reinterpret_cast<__nv_bfloat16*>(wdiag + (tap * 4 + (c >> 4)) * 512 + (n >> 3) * 384 + (n & 7) * 18) =
-            __float2bfloat16_rn(wv);
-    }
-    fence_proxy_async();                   // the tensor core reads these through the async proxy
-    __syncthreads();
-    const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int acc_cols = m_tiles * DTC_CB;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (long long n = 0; n < my_tiles; ++n) {
-                const int s = (int)(n % p.stages);
-                if (n >= p.stages) mbar_wait(&empty_bar[s], (uint32_t)(((n / p.stages) - 1) & 1));
-                const int4 c = decode_tile(p, blockIdx.x + n * (long long)gridDim.x);
-                mbar_expect_tx(&full_bar[s], (uint32_t)p.box_bytes);
-                tma_load_5d(ring + (size_t)s * p.stage_bytes, &tmX, &full_bar[s], c_base, c.w - p.pS, c.z - p.pS,
-                            p.src_first + c.y * p.src_step, c.x);
-            }
-        }
-    } else if (warp <= 4) {
-        // Four MMA issuers, one per 16-channel group: a tcgen05.mma costs its issuing thread ~20 instructions
-        // (descriptor arithmetic, uniform-register moves), far more than the 8 tensor-pipe cycles of an
-        // M128 x N16 x K16 tile, so the issue work is spread over four warps.  Only the low 32 bits of a
-        // descriptor change (start address in 16-byte units): one 32-bit add per operand.
-        if (lane == 0) {
-            const int qg = warp - 1;
-            const uint32_t idesc = make_idesc(128, 16, 0, 0);
-            const uint64_t b0 = make_desc(smem_u32(wdiag) + (uint32_t)qg * 512u, 128, 256, 0);
-            const uint32_t b_hi = (uint32_t)(b0 >> 32), b_lo = (uint32_t)b0;
-            const uint32_t wi8 = (uint32_t)p.Wi * 8u;
-            for (long long n = 0; n < my_tiles; ++n) {
-                const int s = (int)(n % p.stages);
-                const int a = (int)(n & 1);
-                mbar_wait(&tempty_bar[a], (uint32_t)(((n >> 1) & 1) ^ 1));
-                mbar_wait(&full_bar[s], (uint32_t)((n / p.stages) & 1));
-                tc_fence_after();
-                // Start addresses that are not aligned to the 1024-byte swizzle atom keep base-offset 0: the unit
-                // swizzles on absolute shared-memory address bits, exactly like the TMA write did (verified
-                // against the CUDA-core path on ragged shapes).
-                const uint64_t a0 = make_desc(smem_u32(ring + (size_t)s * p.stage_bytes) + (uint32_t)qg * 32u, 16, 1024, 2);
-                const uint32_t a_hi = (uint32_t)(a0 >> 32), a_lo = (uint32_t)a0;
-                const uint32_t d_base = tmem_base + (uint32_t)(a * acc_cols + qg * 16);
-                for (int m = 0; m < m_tiles; ++m) {
-                    const uint32_t d0 = d_base + (uint32_t)(m * DTC_CB);
-                    uint32_t arow = a_lo + (uint32_t)m * 1024u;            // 128 pixels x 8 units
-#pragma unroll
-                    for (int i = 0; i < K; ++i, arow += wi8) {
-#pragma unroll
-                        for (int j = 0; j < K; ++j)
-                            umma_bf16(d0, ((uint64_t)a_hi << 32) | (arow + (uint32_t)(j * 8)),
-                                      ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)((i * K + j) * 128)), idesc, (i | j) != 0);
-                    }
-                }
-                umma_commit(&empty_bar[s]);
-                umma_commit(&tfull_bar[a]);
-            }
-        }
-    } else if (warp >= 8) {
-        const int q = warp & 3;
-        uint8_t* stage_w = staging + q * 4096;
-        // destination frames that exist only because of the temporal padding: zeros, nothing to read
-        if (p.nzf > 0) {
-            const int frame16 = (int)((long long)p.Ho * p.Wo * p.C / 8);
-            const int nframes = p.B * p.nzf, ncta = gridDim.x * gridDim.y;
-            for (int f = blockIdx.y * gridDim.x + blockIdx.x; f < nframes; f += ncta) {
-                uint4* dst = reinterpret_cast<uint4*>(y) + ((long long)(f / p.nzf) * p.To + p.zf[f % p.nzf]) * frame16;
-                for (int e = tid - 256; e < frame16; e += 128) dst[e] = make_uint4(0u, 0u, 0u, 0u);
-            }
-        }
-        const int nchunk = min(8, (p.C - c_base) >> 3);         // valid 16-byte chunks of a pixel's 128-byte row
-        for (long long n = 0; n < my_tiles; ++n) {
-            const int a = (int)(n & 1);
-            const int4 c = decode_tile(p, blockIdx.x + n * (long long)gridDim.x);
-            const int to = p.f_first + c.y * p.f_step;
-            __nv_bfloat16* ybase = y + (((long long)c.x * p.To + to) * p.Ho * p.Wo) * p.C + c_base;
-            mbar_wait(&tfull_bar[a], (uint32_t)((n >> 1) & 1));
-            tc_fence_after();
-            for (int m = 0; m < m_tiles; ++m) {
-                const int pix = m * 128 + q * 32 + lane;           // halo-tile pixel this lane's TMEM row belongs to
-                const int hl = pix / p.Wi, wl = pix - hl * p.Wi;
-                const int ho = c.z + hl, wo = c.w + wl;
-                const bool ok = hl < p.Ht && wl < p.Wt && ho < p.Ho && wo < p.Wo;
-                const long long off = ok ? ((long long)ho * p.Wo + wo) * p.C : -1;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_cols + m * DTC_CB);
-                uint32_t r[4][16];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) tmem_ld16(taddr + (uint32_t)(g * 16), r[g]);
-                tmem_ld_wait();
-                uint8_t* rowp = stage_w + lane * 128;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 o0, o1;
-                    o0.x = pack_bf16x2(__uint_as_float(r[g][0]), __uint_as_float(r[g][1]));
-                    o0.y = pack_bf16x2(__uint_as_float(r[g][2]), __uint_as_float(r[g][3]));
-                    o0.z = pack_bf16x2(__uint_as_float(r[g][4]), __uint_as_float(r[g][5]));
-                    o0.w = pack_bf16x2(__uint_as_float(r[g][6]), __uint_as_float(r[g][7]));
-                    o1.x = pack_bf16x2(__uint_as_float(r[g][8]), __uint_as_float(r[g][9]));
-                    o1.y = pack_bf16x2(__uint_as_float(r[g][10]), __uint_as_float(r[g][11]));
-                    o1.z = pack_bf16x2(__uint_as_float(r[g][12]), __uint_as_float(r[g][13]));
-                    o1.w = pack_bf16x2(__uint_as_float(r[g][14]), __uint_as_float(r[g][15]));
-                    *reinterpret_cast<uint4*>(rowp + (((2 * g) ^ (lane & 7)) << 4)) = o0;
-                    *reinterpret_cast<uint4*>(rowp + (((2 * g + 1) ^ (lane & 7)) << 4)) = o1;
-                }
-                __syncwarp();
-                const int ch = lane & 7, r4 = lane >> 3;
-#pragma unroll
-                for (int s8 = 0; s8 < 8; ++s8) {
-                    const int rr = s8 * 4 + r4;
-                    const long long roff = __shfl_sync(0xffffffffu, off, rr);
-                    if (roff >= 0 && ch < nchunk) {
-                        const uint4 v4 = *reinterpret_cast<const uint4*>(stage_w + rr * 128 + ((ch ^ (rr & 7)) << 4));
-                        *reinterpret_cast<uint4*>(ybase + roff + ch * 8) = v4;
-                    }
-                }
-                __syncwarp();
-            }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[a]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 5) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
-static bool dw_tc_enabled() {
-    static const bool on = [] { const char* e = getenv("PB_DW_TC"); return !(e && e[0] == '0'); }();
-    return on;
-}
-
-// Geometry of the tensor-core path: full-width halo tiles, the tile height that wastes the fewest MMA rows.
-template <int K>
-static bool launch_fwd_tc(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y, const DwDims& d, int pT, int sT,
-                          int flip, cudaStream_t st) {
-    if (!dw_tc_enabled() || d.C < 96) return false;
-    DwTile p;
-    p.B = d.B; p.C = d.C; p.To = d.To; p.Ho = d.Ho; p.Wo = d.Wo; p.pS = d.pH;
-    p.Cb = DTC_CB; p.Gb = DTC_CB / 4; p.nblk = ceil_div(d.C, DTC_CB);
-    p.Wt = d.Wo; p.tiles_w = 1; p.Wi = d.Wo + K - 1;
-    if (p.Wi > 256) return false;
-    int best_ht = 0, best_mt = 0;
-    double best = 0.0;
-    for (int ht = 1; ht <= d.Ho; ++ht) {
-        const int th = ceil_div(d.Ho, ht);
-        if (ceil_div(d.Ho, th) != ht) continue;                       // balanced heights only
-        const int mt = ceil_div((long long)ht * p.Wi, 128);
-        const long long bytes = (long long)(ht + K - 1) * p.Wi * 128;
-        if (mt > DTC_MAX_MT || bytes > 56 * 1024 || ht + K - 1 > 256) break;
-        const double useful = (double)d.Ho * d.Wo;
-        const double score = useful / ((double)th * mt * 128) * (1.0 - 0.15 * (double)(K - 1) / (ht + K - 1));
-        if (score > best) { best = score; best_ht = ht; best_mt = mt; }
-    }
-    if (best_ht == 0) return false;
-    // Every tap re-reads the whole tile from shared memory (128 B/clk): 25 reads per input for a 5x5 filter, a
-    // bound of ~2.5 TB/s times the fraction of MMA rows that are real output pixels.  That beats the CUDA-core
-    // 5x5 kernel (1.2 TB/s) on 28x28 planes, but not on 7x7 planes (40 % useful rows), and never the 3x3 one.
-    if (best < 0.6) return false;
-    p.Ht = best_ht; p.tiles_h = ceil_div(d.Ho, best_ht); p.Hi = best_ht + K - 1;
-    p.box_bytes = p.Hi * p.Wi * 128;
-    p.box2_bytes = 0;
-    // the last MMA tile reads (K-1)*(Wi+1) rows past pixel m_tiles*128: keep that inside the stage
-    const int rows_read = best_mt * 128 + (K - 1) * (p.Wi + 1);
-    p.stage_bytes = (std::max(p.Hi * p.Wi, rows_read) * 128 + 1023) / 1024 * 1024;
-    constexpr int WDIAG_BYTES = K * K * 4 * 512;
-    p.stages = std::min(DWT_MAX_STAGES, (224 * 1024 - WDIAG_BYTES - 4 * 4096 - 1024) / p.stage_bytes);
-    if (p.stages < 2) return false;
-    if (!plan_frames(p, d.To, d.T, sT, -pT, 1)) return false;         // source frame = to*sT - pT
-    p.flip = flip;
-    CUtensorMap tm;
-    {
-        uint64_t dims[5] = {(uint64_t)d.C, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.T, (uint64_t)d.B};
-        uint64_t str[5] = {2, (uint64_t)d.C * 2, (uint64_t)d.W * d.C * 2, (uint64_t)d.H * d.W * d.C * 2,
-                           (uint64_t)d.T * d.H * d.W * d.C * 2};
-        uint32_t box[5] = {(uint32_t)DTC_CB, (uint32_t)p.Wi, (uint32_t)p.Hi, 1, 1};
-        if (make_tmap_bf16(&tm, x, 5, dims, str, box, 128) != PB_OK) return false;
-    }
-    static std::once_flag once;
-    std::call_once(once, [] {
-        cudaFuncSetAttribute(dw_fwd_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    });
-    const size_t smem = (size_t)p.stages * p.stage_bytes + WDIAG_BYTES + 4 * 4096 + 1024;
-    int ctas = std::max(1, 148 / p.nblk);
-    ctas = (int)std::min<long long>(ctas, std::max<long long>(p.ntiles, 1));
-    (void)launch_pdl(dw_fwd_tc_kernel<K>, dim3(ctas, p.nblk), dim3(DTC_THREADS), smem, st, tm, w_tc, y, p, best_mt);
     return true;
 }
 
@@ -899,12 +696,12 @@ static bool strip7(int wo) { return wo % 7 == 0; }
 template <> bool dw_fwd_tiled<__nv_bfloat16>(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y,
                                             const DwDims& d, cudaStream_t st) {
     if (!mobilenet_class(d) || !aligned16(x, y)) return false;
-    if (d.sH == 1 && d.kH == 5 && launch_fwd_tc<5>(x, w_tc, y, d, d.pT, d.sT, 0, st)) return true;
     if (d.kH == 3 && d.sH == 1)
         return strip7(d.Wo) ? launch_fwd<3, 1, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st) : launch_fwd<3, 1, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
     if (d.kH == 3 && d.sH == 2)
         return strip7(d.Wo) ? launch_fwd<3, 2, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st) : launch_fwd<3, 2, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
-    if (d.kH == 5 && d.sH == 1) return launch_fwd<5, 1, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
+    if (d.kH == 5 && d.sH == 1)
+        return strip7(d.Wo) ? launch_fwd<5, 1, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st) : launch_fwd<5, 1, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
     if (d.kH == 5 && d.sH == 2) return launch_fwd<5, 2, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
     return false;
 }
@@ -922,10 +719,9 @@ template <> bool dw_dgrad_tiled<__nv_bfloat16>(const __nv_bfloat16* dy, const fl
     DwDims r = d;                      // roles swapped: "input" = dy (To,Ho,Wo), "output" = dx (T,H,W)
     r.T = d.To; r.H = d.Ho; r.W = d.Wo;
     r.To = d.T; r.Ho = d.H; r.Wo = d.W;
-    if (d.kH == 5 && launch_fwd_tc<5>(dy, w_tc, dx, r, -d.pT, 1, 1, st)) return true;
     if (d.kH == 3)
         return strip7(r.Wo) ? launch_fwd<3, 1, 7>(dy, w_tc, dx, r, -d.pT, 1, 1, st) : launch_fwd<3, 1, 4>(dy, w_tc, dx, r, -d.pT, 1, 1, st);
-    return launch_fwd<5, 1, 4>(dy, w_tc, dx, r, -d.pT, 1, 1, st);
+    return strip7(r.Wo) ? launch_fwd<5, 1, 7>(dy, w_tc, dx, r, -d.pT, 1, 1, st) : launch_fwd<5, 1, 4>(dy, w_tc, dx, r, -d.pT, 1, 1, st);
 }
 
 template <> bool dw_wgrad_tiled<__nv_bfloat16>(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw_tc,

@@ -38,9 +38,9 @@ DW_CASES = [
     (1, 240, 7, 6, 6, (5, 3, 3), (1, 2, 2), (2, 1, 1)),       # movinet 5x3x3
     (1, 960, 3, 7, 7, (1, 5, 5), (1, 1, 1), (2, 2, 2)),       # widest layer
     (2, 8, 1, 1, 1, (1, 3, 3), (1, 1, 1), (1, 1, 1)),         # degenerate 1x1x1 frame
-    (2, 104, 3, 12, 26, (1, 5, 5), (1, 1, 1), (2, 2, 2)),      # tensor-core path (5x5, stride 1, C >= 96): ragged channel block
-    (1, 184, 2, 30, 17, (1, 5, 5), (1, 1, 1), (2, 2, 2)),      # ... odd width, ragged last tile row
-    (1, 128, 2, 40, 60, (1, 5, 5), (1, 1, 1), (2, 2, 2)),      # ... two MMA tiles per halo tile
+    (2, 104, 3, 12, 26, (1, 5, 5), (1, 1, 1), (2, 2, 2)),      # 5x5 stride 1, ragged channel block (C = 104 = 64 + 40)
+    (1, 184, 2, 30, 17, (1, 5, 5), (1, 1, 1), (2, 2, 2)),      # ... odd width, strips of 4
+    (1, 128, 2, 40, 60, (1, 5, 5), (1, 1, 1), (2, 2, 2)),      # ... wide rows, several w-tiles
     # MobileNetLarge3D's own layer shapes, 2 clips
     (2, 16, 8, 112, 112, (1, 3, 3), (1, 1, 1), (1, 1, 1)),    # block2.0
     (2, 64, 10, 112, 112, (1, 3, 3), (2, 2, 2), (1, 1, 1)),   # block2.1
