@@ -537,6 +537,18 @@ static bool plan_tile(const PlanIn& in, DwTile& p) {
     p.pS = in.pS;
     p.nblk = ceil_div(in.C, 128);
     p.Cb = (ceil_div(in.C, p.nblk) + 7) / 8 * 8;
+    if (in.with_dst_tile && in.C > 128) {
+        // weight gradient: a thread is (4 channels, filter row), so only multiples of Gb*K threads work; pick the
+        // channel block (>= 64 channels: 128-byte TMA rows) that keeps most of the consumer threads busy
+        double best = 0.0;
+        for (int cb = 64; cb <= 128; cb += 8) {
+            const int lanes = cb / 4 * in.K;
+            if (lanes > DWT_CONSUMERS) continue;
+            const int nb = ceil_div(in.C, cb);
+            const double util = (double)(DWT_CONSUMERS / lanes * lanes) / DWT_CONSUMERS * in.C / ((double)nb * cb);
+            if (util > best + 1e-9) { best = util; p.Cb = cb; }
+        }
+    }
     p.nblk = ceil_div(in.C, p.Cb);
     p.Gb = p.Cb / 4;
     const int K = in.K, S = in.S, WS = in.WS;
@@ -731,7 +743,8 @@ template <> bool dw_wgrad_tiled<__nv_bfloat16>(const __nv_bfloat16* x, const __n
         return strip7(d.Wo) ? launch_wgrad<3, 1, 7>(x, dy, dw_tc, d, st) : launch_wgrad<3, 1, 4>(x, dy, dw_tc, d, st);
     if (d.kH == 3 && d.sH == 2)
         return strip7(d.Wo) ? launch_wgrad<3, 2, 7>(x, dy, dw_tc, d, st) : launch_wgrad<3, 2, 4>(x, dy, dw_tc, d, st);
-    if (d.kH == 5 && d.sH == 1) return launch_wgrad<5, 1, 4>(x, dy, dw_tc, d, st);
+    if (d.kH == 5 && d.sH == 1)
+        return strip7(d.Wo) ? launch_wgrad<5, 1, 7>(x, dy, dw_tc, d, st) : launch_wgrad<5, 1, 4>(x, dy, dw_tc, d, st);
     if (d.kH == 5 && d.sH == 2) return launch_wgrad<5, 2, 4>(x, dy, dw_tc, d, st);
     return false;
 }
