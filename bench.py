@@ -342,8 +342,16 @@ def main():
                              "alg_bytes_per_launch": v["bytes"] / v["launches"]}
         top = next(iter(kernels))
         kt = kernels[top]
+        # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this same command
+        # (profiles/roofline_traffic.json; null if that kernel has no capture)
+        traffic = None
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "roofline_traffic.json")) as f:
+                traffic = json.load(f).get(top, {}).get("dram_bytes_per_launch")
+        except OSError:
+            pass
         roofline = {"kernel": top, "bound": "hbm", "achieved": kt["GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": kt["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_kind + " copy bandwidth",
+                    "frac": kt["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_kind + " copy bandwidth",
                     "share_of_step": kt["share"], "avg_launch_us": kt["avg_us"],
                     "alg_bytes_per_launch": kt["alg_bytes_per_launch"]}
         dw = {k: v for k, v in kernels.items() if k.startswith("pb_dwconv3d")}
