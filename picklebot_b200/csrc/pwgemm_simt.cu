@@ -166,17 +166,25 @@ __global__ void cast_matrix_kernel(const float* __restrict__ src, TD* __restrict
     dst[o] = from_float<TD>(v);
 }
 
+// 8 consecutive k per thread: two float4 loads of W and of the gate, one 16-byte bf16 store
 __global__ void fold_gate_kernel(const float* __restrict__ W, const float* __restrict__ gate,
-                                 __nv_bfloat16* __restrict__ dst, int N, int K, long long total) {
+                                 __nv_bfloat16* __restrict__ dst, int N, int K, long long total8) {
     pdl_trigger();
     pdl_wait();
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    int k = (int)(idx % K);
-    long long q = idx / K;
-    int n = (int)(q % N);
-    int b = (int)(q / N);
-    dst[idx] = __float2bfloat16_rn(W[(long long)n * K + k] * gate[(long long)b * K + k]);
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total8) return;
+    const int K8 = K >> 3;
+    const int k = (int)(idx % K8) << 3;
+    const long long q = idx / K8;
+    const int n = (int)(q % N);
+    const int b = (int)(q / N);
+    const float4* wp = reinterpret_cast<const float4*>(W + (long long)n * K + k);
+    const float4* gp = reinterpret_cast<const float4*>(gate + (long long)b * K + k);
+    const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), g0 = __ldg(gp), g1 = __ldg(gp + 1);
+    uint4 o;
+    o.x = pack_bf16x2(w0.x * g0.x, w0.y * g0.y); o.y = pack_bf16x2(w0.z * g0.z, w0.w * g0.w);
+    o.z = pack_bf16x2(w1.x * g1.x, w1.y * g1.y); o.w = pack_bf16x2(w1.z * g1.z, w1.w * g1.w);
+    *reinterpret_cast<uint4*>(dst + idx * 8) = o;
 }
 
 // dst[(i*N + n)][(j*K + k)] = (i == j) ? W[n][k] : 0  -- the weight of a row-folded GEMM (pwgemm_tc.cu)
@@ -248,8 +256,10 @@ extern "C" int pb_cast_matrix(const float* src, void* dst, int dst_dtype, int ro
 
 extern "C" int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, int Bt, int N, int K,
                                  pb_stream_t stream) {
-    PB_REQUIRE(W && gate && dst && Bt > 0 && N > 0 && K > 0, "fold_gate: bad args");
-    long long n = (long long)Bt * N * K;
+    PB_REQUIRE(W && gate && dst && Bt > 0 && N > 0 && K > 0 && K % 8 == 0, "fold_gate: bad args (K %% 8 == 0)");
+    PB_REQUIRE(((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(gate) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0,
+               "fold_gate: pointers must be 16-byte aligned");
+    long long n = (long long)Bt * N * (K / 8);
     (void)launch_pdl(fold_gate_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, W, gate, (__nv_bfloat16*)dst, N, K, n);
     PB_CHECK_LAUNCH("fold_gate_kernel");
     return PB_OK;
