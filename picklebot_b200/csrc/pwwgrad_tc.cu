@@ -324,21 +324,43 @@ wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__
     }
 }
 
-// dgate[b][k] = sum_n W[n][k] * P_b[n][k],  P_b = sum_c partial[b][c]
-__global__ void wgrad_dgate_kernel(const float* __restrict__ partial, const float* __restrict__ W,
-                                   float* __restrict__ dgate, int Bt, int chunks, int N, int K) {
+// dgate[b][k] = sum_n W[n][k] * P_b[n][k],  P_b = sum_c partial[b][c].
+// blockDim = (32 k, 8 slices of the chunks*N rows); shared-memory reduction over the slices.
+__global__ void __launch_bounds__(256)
+wgrad_dgate_kernel(const float* __restrict__ partial, const float* __restrict__ W,
+                   float* __restrict__ dgate, int Bt, int chunks, int N, int K) {
+    __shared__ float red[8][33];
     pdl_trigger();
     pdl_wait();
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + kl;
     const int b = blockIdx.y;
-    if (k >= K) return;
     const long long NK = (long long)N * K;
     float acc = 0.f;
-    for (int c = 0; c < chunks; ++c) {
-        const float* pb = partial + ((long long)b * chunks + c) * NK;
-        for (int n = 0; n < N; ++n) acc = fmaf(W[(long long)n * K + k], pb[(long long)n * K + k], acc);
+    if (k < K) {
+        for (int c = 0; c < chunks; ++c) {
+            const float* pb = partial + ((long long)b * chunks + c) * NK + k;
+            const float* wk = W + k;
+            int n = sl;
+            for (; n + 24 < N; n += 32) {                   // four rows in flight per thread
+                const float p0 = pb[(long long)n * K], p1 = pb[(long long)(n + 8) * K];
+                const float p2 = pb[(long long)(n + 16) * K], p3 = pb[(long long)(n + 24) * K];
+                acc = fmaf(__ldg(wk + (long long)n * K), p0, acc);
+                acc = fmaf(__ldg(wk + (long long)(n + 8) * K), p1, acc);
+                acc = fmaf(__ldg(wk + (long long)(n + 16) * K), p2, acc);
+                acc = fmaf(__ldg(wk + (long long)(n + 24) * K), p3, acc);
+            }
+            for (; n < N; n += 8) acc = fmaf(__ldg(wk + (long long)n * K), pb[(long long)n * K], acc);
+        }
     }
-    dgate[(long long)b * K + k] = acc;
+    red[sl][kl] = acc;
+    __syncthreads();
+    if (sl == 0 && k < K) {
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v += red[i][kl];
+        dgate[(long long)b * K + k] = v;
+    }
 }
 
 }  // namespace tc
@@ -398,8 +420,8 @@ extern "C" int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, 
                        pl.chunks * pl.fold, N, K));
     PB_CHECK_LAUNCH("wgrad_reduce_kernel");
     if (dgate) {
-        dim3 g2(ceil_div(K, 128), Bt);
-        PB_CUDA(launch_pdl(wgrad_dgate_kernel, g2, dim3(128), 0, st, (const float*)p.partial, Wf32, dgate, Bt,
+        dim3 g2(ceil_div(K, 32), Bt);
+        PB_CUDA(launch_pdl(wgrad_dgate_kernel, g2, dim3(256), 0, st, (const float*)p.partial, Wf32, dgate, Bt,
                            pl.chunks * pl.fold, N, K));
         PB_CHECK_LAUNCH("wgrad_dgate_kernel");
     }
