@@ -141,11 +141,7 @@ def test_train_step_fp32(model):
             assert int(after[k]) == int(v) == 1
 
 
-@pytest.mark.parametrize("model", MODEL_NAMES)
-def test_train_step_bf16_autocast(model):
-    g = golden(model)
-    nc = g["num_classes"]
-    shape = g["train_shape"]
+def _check_train_step_bf16(model: str, shape, nc: int):
     m = build(model, nc)
     clips = synth.synthetic_clips_u8(*shape).cuda()
     x = synth.clips_to_features(clips, torch.bfloat16)
@@ -163,12 +159,26 @@ def test_train_step_bf16_autocast(model):
     cat = lambda d: torch.cat([d[k].detach().float().cpu().flatten() for k in names])
     e_log, e_log_ref = rel_err(logits, t_logits), rel_err(r_logits.float(), t_logits)
     e_g, e_g_ref = rel_err(cat(grads), cat(t_grads)), rel_err(cat(r_grads), cat(t_grads))
-    print(f"\n{model}: bf16 train step vs fp32 truth: logits ours {e_log:.2e} / torch-autocast {e_log_ref:.2e}; "
-          f"grads ours {e_g:.2e} / torch-autocast {e_g_ref:.2e}; ours vs torch-autocast logits "
+    print(f"\n{model} {tuple(shape)}: bf16 train step vs fp32 truth: logits ours {e_log:.2e} / torch-autocast "
+          f"{e_log_ref:.2e}; grads ours {e_g:.2e} / torch-autocast {e_g_ref:.2e}; ours vs torch-autocast logits "
           f"{rel_err(logits, r_logits.float()):.2e} grads {rel_err(cat(grads), cat(r_grads)):.2e}")
     assert e_log < max(1e-2, 1.5 * e_log_ref) and abs(loss - float(t_loss)) < max(1e-2, 2 * abs(float(r_loss) - float(t_loss)))
     # gradients: within 1e-2 of the fp32 truth, or at least as close to it as torch's own bf16 path is
     assert e_g < max(1e-2, 1.5 * e_g_ref)
+
+
+@pytest.mark.parametrize("model", MODEL_NAMES)
+def test_train_step_bf16_autocast(model):
+    g = golden(model)
+    _check_train_step_bf16(model, g["train_shape"], g["num_classes"])
+
+
+@pytest.mark.parametrize("model,shape", [("MobileNetLarge3D", (4, 16, 224, 224)),      # BASELINE.json configs[2] clips
+                                         ("MobileNetSmall3D", (2, 32, 224, 224))])     # configs[4]: long clips
+def test_train_step_bf16_full_size_clips(model, shape):
+    """The benchmark's own clip shape (and the long-clip stress shape) through every full-size kernel path:
+    row-folded GEMMs, TMA-tiled depthwise layers at 112/56/28/14/7 pixels, fused statistics."""
+    _check_train_step_bf16(model, shape, golden(model)["num_classes"])
 
 
 def test_bottleneck_module_standalone_and_strides():
