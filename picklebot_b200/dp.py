@@ -50,10 +50,16 @@ class GradientBuckets:
     buckets, as torch DDP does.  A hook on every parameter fires after its gradient was accumulated; when a
     bucket is complete its gradients are copied into one flat fp32 buffer and an asynchronous all-reduce is
     launched.  ``finish()`` waits, divides by the world size and copies the averages back into ``.grad``.
+
+    ``grad_as_bucket_view=True`` (what torch DDP calls gradient_as_bucket_view) makes every ``.grad`` a view into
+    its bucket's flat buffer for good: autograd accumulates straight into the bucket, the all-reduce runs in
+    place and nothing is packed or unpacked (~340 small copy kernels per step for MobileNetLarge3D otherwise).
+    Use ``zero_grad()`` of this object then (one fill per bucket, and the views survive), not
+    ``optimizer.zero_grad(set_to_none=True)``.
     """
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group=None, bucket_cap_mb: float = 25.0,
-                 first_bucket_mb: float = 1.0):
+                 first_bucket_mb: float = 1.0, grad_as_bucket_view: bool = False):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
@@ -75,8 +81,38 @@ class GradientBuckets:
         self._pending = [0] * len(self.buckets)
         self._work: List[Optional[object]] = [None] * len(self.buckets)
         self._sync = True
+        self.grad_as_bucket_view = grad_as_bucket_view
+        if grad_as_bucket_view:
+            for i, bucket in enumerate(self.buckets):
+                flat = torch.zeros(sum(p.numel() for p in bucket), dtype=torch.float32, device=bucket[0].device)
+                self._flat[i] = flat
+                off = 0
+                for p in bucket:
+                    view = flat[off:off + p.numel()].view_as(p)
+                    if p.grad is not None:
+                        view.copy_(p.grad)
+                    p.grad = view
+                    off += p.numel()
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self.reset()
+
+    def zero_grad(self) -> None:
+        """Zero all gradients; with bucket views that is one fill per bucket."""
+        if self.grad_as_bucket_view:
+            for flat in self._flat:
+                flat.zero_()
+        else:
+            for p in self.params:
+                if p.grad is not None:
+                    p.grad.zero_()
+
+    def reduce_all(self) -> None:
+        """Launch the all-reduce of every bucket now, for callers that produced the gradients without the hooks
+        firing (under ``no_sync()``, e.g. by replaying a captured CUDA graph).  Follow with ``finish()``."""
+        for i in range(len(self.buckets)):
+            if self._work[i] is None:
+                self._pending[i] = 0
+                self._launch(i)
 
     def reset(self) -> None:
         self._pending = [len(b) for b in self.buckets]
@@ -103,13 +139,14 @@ class GradientBuckets:
         bucket = self.buckets[i]
         n = sum(p.numel() for p in bucket)
         flat = self._flat[i]
-        if flat is None or flat.device != bucket[0].device:
-            flat = torch.empty(n, dtype=torch.float32, device=bucket[0].device)
-            self._flat[i] = flat
-        off = 0
-        for p in bucket:
-            flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
-            off += p.numel()
+        if not self.grad_as_bucket_view:
+            if flat is None or flat.device != bucket[0].device:
+                flat = torch.empty(n, dtype=torch.float32, device=bucket[0].device)
+                self._flat[i] = flat
+            off = 0
+            for p in bucket:
+                flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+                off += p.numel()
         if self.world > 1:
             self._work[i] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         else:
@@ -130,10 +167,11 @@ class GradientBuckets:
             flat = self._flat[i]
             if self.world > 1:
                 flat.div_(self.world)
-            off = 0
-            for p in bucket:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
-                off += p.numel()
+            if not self.grad_as_bucket_view:
+                off = 0
+                for p in bucket:
+                    p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                    off += p.numel()
         self.reset()
 
     def remove(self) -> None:

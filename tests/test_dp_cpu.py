@@ -31,7 +31,7 @@ def _data(n=16):
     return torch.rand(n, 12, generator=g), torch.randint(0, 5, (n,), generator=g)
 
 
-def _worker(rank, world, port, accum, out):
+def _worker(rank, world, port, accum, out, views=False, deferred=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -44,17 +44,25 @@ def _worker(rank, world, port, accum, out):
         dp.broadcast_module(model)
         x, y = _data()
         micro = 16 // (world * accum)
-        buckets = dp.GradientBuckets(model.parameters(), bucket_cap_mb=0.5, first_bucket_mb=0.01)
+        buckets = dp.GradientBuckets(model.parameters(), bucket_cap_mb=0.5, first_bucket_mb=0.01,
+                                     grad_as_bucket_view=views)
         assert len(buckets.buckets) >= 3
         ranges = dp.shard_range(rank, world, 16, micro)
-        for i, (a, b) in enumerate(ranges):
-            loss = torch.nn.functional.cross_entropy(model(x[a:b]), y[a:b]) / accum
-            if i + 1 < len(ranges):
-                with buckets.no_sync():
+        for step in range(2 if views else 1):           # second step: zero_grad() keeps the views and re-arms
+            buckets.zero_grad()
+            for i, (a, b) in enumerate(ranges):
+                loss = torch.nn.functional.cross_entropy(model(x[a:b]), y[a:b]) / accum
+                if deferred or i + 1 < len(ranges):     # deferred: gradients produced without the hooks firing
+                    with buckets.no_sync():
+                        loss.backward()
+                else:
                     loss.backward()
-            else:
-                loss.backward()
-        buckets.finish()
+            if deferred:
+                buckets.reduce_all()
+            buckets.finish()
+        if views:
+            for b, flat in zip(buckets.buckets, buckets._flat):
+                assert all(p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for p in b)
         if rank == 0:
             torch.save({k: p.grad.clone() for k, p in model.named_parameters()}, out)
         # a second step must work too (buckets re-armed), and all ranks must hold identical gradients
@@ -66,11 +74,14 @@ def _worker(rank, world, port, accum, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("accum", [1, 2])
-def test_bucketed_gradient_average_matches_shard_emulation(tmp_path, accum):
+@pytest.mark.parametrize("accum,views,deferred", [(1, False, False), (2, False, False), (2, True, False), (1, True, True),
+                                                  (2, True, True)])
+def test_bucketed_gradient_average_matches_shard_emulation(tmp_path, accum, views, deferred):
+    """views: .grad tensors are views into the bucket buffers (no pack/unpack); deferred: all buckets reduced by
+    reduce_all() after the backward passes (how the captured-graph training step exchanges gradients)."""
     world = 2
     out = str(tmp_path / "grads.pt")
-    mp.spawn(_worker, args=(world, _free_port(), accum, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), accum, out, views, deferred), nprocs=world, join=True)
     got = torch.load(out)
     # emulation: every (rank, micro-batch) shard through the same model separately, local mean loss / accum,
     # gradients summed over micro-batches and averaged over ranks (BatchNorm statistics are per shard)
