@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--profile-steps", type=int, default=1)
     ap.add_argument("--dp", default="buckets", choices=["buckets", "ddp"],
                     help="gradient exchange for N>1: picklebot_b200.dp.GradientBuckets or torch DDP")
+    ap.add_argument("--no-graphs", action="store_true",
+                    help="issue every micro-batch eagerly instead of replaying picklebot_b200.graph.GraphedTrainStep")
     return ap.parse_args()
 
 
@@ -207,15 +209,42 @@ def main():
         else:
             from picklebot_b200 import dp as pbdp
             pbdp.broadcast_module(model)
-            buckets = pbdp.GradientBuckets(model.parameters())
+            buckets = pbdp.GradientBuckets(model.parameters(), grad_as_bucket_view=True)
     opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=5e-4, fused=True)
+    use_graph = not args.no_graphs and args.dp == "buckets"
 
     # synthetic uint8 clips: this rank's shard of each global batch, distinct per micro-batch
     clips = [synth.synthetic_clips_u8_device(micro, *CLIP, seed=1000 * rank + a, device=dev) for a in range(accum)]
     labels = [synth.synthetic_labels(micro, NUM_CLASSES, seed=77 + 1000 * rank + a).to(dev) for a in range(accum)]
     loss_buf = torch.zeros((), device=dev)
 
-    def micro_step(x_u8, y, sync_grads):
+    # One micro-batch = forward + loss + backward.  Default: captured once in a CUDA graph and replayed (issuing the
+    # ~370 launches from Python costs the host ~11 ms per 14 ms of GPU work, which starves the GPUs once eight
+    # processes share the box's cores); gradients accumulate in place, the exchange runs after the last replay.
+    gstep = None
+    if use_graph:
+        from contextlib import nullcontext
+        from picklebot_b200.graph import GraphedTrainStep
+        with (buckets.no_sync() if buckets is not None else nullcontext()):
+            gstep = GraphedTrainStep(model, clips[0].permute(0, 4, 1, 2, 3), labels[0],
+                                     loss_fn=lambda logits, y: F.cross_entropy(logits.float(), y) / accum)
+        grad_list = [p.grad for p in model.parameters() if p.grad is not None]
+
+    def zero_grads():
+        if gstep is None:
+            opt.zero_grad(set_to_none=True)
+        elif buckets is not None:
+            buckets.zero_grad()                 # one fill per bucket; .grad tensors are views of the buckets
+        else:
+            torch._foreach_zero_(grad_list)     # the graph accumulates into these very tensors
+
+    def micro_step(x_u8, y, sync_grads, eager=False):
+        if gstep is not None and not eager:
+            loss = gstep(x_u8.permute(0, 4, 1, 2, 3), y)
+            if sync_grads and buckets is not None:
+                buckets.reduce_all()
+                buckets.finish()
+            return loss
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = net(x_u8.permute(0, 4, 1, 2, 3))        # (B,3,T,H,W) view of the uint8 NTHWC batch
             loss = F.cross_entropy(logits.float(), y) / accum
@@ -228,13 +257,13 @@ def main():
                 buckets.finish()            # wait for the bucketed all-reduces, averaged grads back in .grad
         return loss.detach()
 
-    def step_resident():
+    def step_resident(eager=False):
         tot = None
         for a in range(accum):
-            l = micro_step(clips[a], labels[a], a == accum - 1)
+            l = micro_step(clips[a], labels[a], a == accum - 1, eager)
             tot = l if tot is None else tot + l
         opt.step()
-        opt.zero_grad(set_to_none=True)
+        zero_grads()
         return tot
 
     def barrier():
@@ -265,6 +294,8 @@ def main():
     n0 = _lib.launch_count()
     ms = timed(step_resident, args.steps)
     launches = _lib.launch_count() - n0
+    if gstep is not None:                       # replays launch the captured kernels without passing the C ABI
+        launches += args.steps * accum * gstep.launches
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = args.global_batch / (ms_per_step / 1000.0)
@@ -301,7 +332,7 @@ def main():
                 consumed[slot].record(cur)
                 tot = l if tot is None else tot + l
             opt.step()
-            opt.zero_grad(set_to_none=True)
+            zero_grads()
             host_loss.copy_(tot, non_blocking=True)
             torch.cuda.current_stream().synchronize()          # the user reads the loss every step
             return float(host_loss)
@@ -322,7 +353,7 @@ def main():
         prof = _lib.KernelProfiler()
         _lib.PROFILER = prof
         for _ in range(max(1, args.profile_steps)):
-            step_resident()
+            step_resident(eager=True)           # events around every C-ABI call need the eager path
         _lib.PROFILER = None
         summ = prof.summary()
         if os.environ.get("PB_BENCH_DETAIL"):
@@ -378,10 +409,15 @@ def main():
                        "global_batch": args.global_batch, "micro_batch_per_gpu": micro, "accum_steps": accum,
                        "parallelism": f"dp{world}",
                        "gradient_exchange": ("none (1 GPU)" if world == 1 else
-                                             "picklebot_b200.dp.GradientBuckets: bucketed async NCCL all-reduce from "
-                                             "post-accumulate-grad hooks, once per optimizer step" if args.dp == "buckets"
+                                             "picklebot_b200.dp.GradientBuckets: .grad tensors are views of the bucket "
+                                             "buffers, in-place NCCL all-reduce once per optimizer step" + (
+                                                 " after the last graph replay" if gstep is not None else
+                                                 ", launched from post-accumulate-grad hooks") if args.dp == "buckets"
                                              else "torch DDP, no_sync on all but the last micro-batch"),
-"optimizer": "torch.optim.AdamW(fused=True) inside the timed region",
+                       "launch": ("forward+loss+backward of a micro-batch captured once in a CUDA graph "
+                                  "(picklebot_b200.graph.GraphedTrainStep) and replayed; clips are copied device-to-"
+                                  "device into the graph's static input" if gstep is not None else "eager"),
+                       "optimizer": "torch.optim.AdamW(fused=True) inside the timed region",
                        "l2": "inputs larger than L2 (154 MB uint8 per micro-batch, distinct buffers); no flush",
                        "num_classes": NUM_CLASSES},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
