@@ -13,6 +13,7 @@ scaling is "strong"; the per-GPU micro-batch stays 64 so BatchNorm statistics do
 value   clips/s with the uint8 clips already resident in HBM (distinct buffers per micro-batch, 154 MB each,
         i.e. larger than the 126 MB L2, so no cache flush is needed between iterations).
 e2e     the same step fed from pinned HOST memory through the public module API: per micro-batch H2D copy
+        (issued one micro-batch ahead on a side stream, across step boundaries too, like a prefetching loader)
         of the uint8 clip batch + labels (on a side stream, double buffered) and a D2H read of the loss.
 roofline  per-kernel-family GB/s from CUDA events recorded around every C-ABI launch on the launching
         stream (separate instrumented steps after the timed region), against MEASURED_PEAKS.json.
@@ -319,18 +320,19 @@ def main():
                 lbuf[slot].copy_(host_labels[a], non_blocking=True)
                 ready[slot].record(copy_stream)
 
+        seq = [0]      # running micro-batch number: its buffer slot is seq & 1, uploaded one micro-batch ahead
+
         def step_e2e():
             cur = torch.cuda.current_stream()
-            upload(0, 0)
             tot = None
             for a in range(accum):
-                slot = a & 1
-                if a + 1 < accum:
-                    upload(a + 1, (a + 1) & 1)
+                slot = seq[0] & 1
+                upload((a + 1) % accum, slot ^ 1)      # prefetch the next micro-batch (possibly the next step's first)
                 cur.wait_event(ready[slot])
                 l = micro_step(dbuf[slot], lbuf[slot], a == accum - 1)
                 consumed[slot].record(cur)
                 tot = l if tot is None else tot + l
+                seq[0] += 1
             opt.step()
             zero_grads()
             host_loss.copy_(tot, non_blocking=True)
@@ -339,6 +341,7 @@ def main():
 
         for s in range(2):
             consumed[s].record(torch.cuda.current_stream())
+        upload(0, 0)                                           # the pipeline starts one upload ahead
         step_e2e()
         ms_e = timed(step_e2e, args.steps) / args.steps
         e2e = {"value": args.global_batch / (ms_e / 1000.0), "unit": "clips/s",
