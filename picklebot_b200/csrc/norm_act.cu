@@ -310,7 +310,8 @@ extern "C" int pb_bn_finalize(const double* sums, long long M, const float* gamm
                               float* scale, float* shift, float* mean, float* invstd, int C, pb_stream_t stream) {
     PB_REQUIRE(scale && shift && C > 0, "bn_finalize: bad args");
     PB_REQUIRE(training ? (sums != nullptr && M > 0) : (running_mean && running_var), "bn_finalize: missing statistics");
-    (void)launch_pdl(bn_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, (double)M, gamma, beta, running_mean, running_var, training, momentum, eps, scale, shift, mean, invstd, C);
+    (void)launch_pdl(bn_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, (double)M,
+                     gamma, beta, running_mean, running_var, training, momentum, eps, scale, shift, mean, invstd, C);
     PB_CHECK_LAUNCH("bn_finalize");
     return PB_OK;
 }
@@ -322,7 +323,8 @@ extern "C" int pb_bn_act_fwd(const void* z, const float* scale, const float* shi
     PB_REQUIRE(M < (1LL << 31) && R < (1LL << 31), "bn_act_fwd: too many rows");
     const int grid = row_grid(M, C);
     PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
-        (void)launch_pdl(bn_act_fwd_kernel<T, ACT>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)z, scale, shift, mask, (T*)out, (unsigned)M, (unsigned)R, C, slope);
+        (void)launch_pdl(bn_act_fwd_kernel<T, ACT>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)z,
+                         scale, shift, mask, (T*)out, (unsigned)M, (unsigned)R, C, slope);
     }));
     PB_CHECK_LAUNCH("bn_act_fwd");
     return PB_OK;
@@ -342,9 +344,11 @@ extern "C" int pb_bn_act_bwd_reduce(const void* dout, int dout_bcast, const void
     const size_t smem = 0;
     PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
         if (dout_bcast)
-            (void)launch_pdl(bn_bwd_reduce_kernel<T, ACT, true>, dim3(grid), dim3(256), smem, st, dout, (const T*)z, scale, shift, mean, invstd, mask, sums, (unsigned)M, (unsigned)R, C, slope);
+            (void)launch_pdl(bn_bwd_reduce_kernel<T, ACT, true>, dim3(grid), dim3(256), smem, st, dout, (const T*)z,
+                             scale, shift, mean, invstd, mask, sums, (unsigned)M, (unsigned)R, C, slope);
         else
-            (void)launch_pdl(bn_bwd_reduce_kernel<T, ACT, false>, dim3(grid), dim3(256), smem, st, dout, (const T*)z, scale, shift, mean, invstd, mask, sums, (unsigned)M, (unsigned)R, C, slope);
+            (void)launch_pdl(bn_bwd_reduce_kernel<T, ACT, false>, dim3(grid), dim3(256), smem, st, dout, (const T*)z,
+                             scale, shift, mean, invstd, mask, sums, (unsigned)M, (unsigned)R, C, slope);
     }));
     PB_CHECK_LAUNCH("bn_act_bwd_reduce");
     return PB_OK;
@@ -353,7 +357,8 @@ extern "C" int pb_bn_act_bwd_reduce(const void* dout, int dout_bcast, const void
 extern "C" int pb_bn_bwd_finalize(const double* sums, long long M, int training, float* dgamma, float* dbeta,
                                   float* coef, int C, pb_stream_t stream) {
     PB_REQUIRE(sums && coef && M > 0 && C > 0, "bn_bwd_finalize: bad args");
-    (void)launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, (double)M, training, dgamma, dbeta, coef, C);
+    (void)launch_pdl(bn_bwd_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums,
+                     (double)M, training, dgamma, dbeta, coef, C);
     PB_CHECK_LAUNCH("bn_bwd_finalize");
     return PB_OK;
 }
@@ -370,9 +375,11 @@ extern "C" int pb_bn_act_bwd_apply(const void* dout, int dout_bcast, const void*
     cudaStream_t st = (cudaStream_t)stream;
     PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
         if (dout_bcast)
-            (void)launch_pdl(bn_bwd_apply_kernel<T, ACT, true>, dim3(grid), dim3(256), 0, st, dout, (const T*)z, scale, shift, mean, invstd, mask, coef, (T*)dz, (unsigned)M, (unsigned)R, C, slope);
+            (void)launch_pdl(bn_bwd_apply_kernel<T, ACT, true>, dim3(grid), dim3(256), 0, st, dout, (const T*)z,
+                             scale, shift, mean, invstd, mask, coef, (T*)dz, (unsigned)M, (unsigned)R, C, slope);
         else
-            (void)launch_pdl(bn_bwd_apply_kernel<T, ACT, false>, dim3(grid), dim3(256), 0, st, dout, (const T*)z, scale, shift, mean, invstd, mask, coef, (T*)dz, (unsigned)M, (unsigned)R, C, slope);
+            (void)launch_pdl(bn_bwd_apply_kernel<T, ACT, false>, dim3(grid), dim3(256), 0, st, dout, (const T*)z,
+                             scale, shift, mean, invstd, mask, coef, (T*)dz, (unsigned)M, (unsigned)R, C, slope);
     }));
     PB_CHECK_LAUNCH("bn_act_bwd_apply");
     return PB_OK;

@@ -212,7 +212,8 @@ extern "C" int pb_pw_gemm_simt(const void* A, const float* W, long long w_sn, lo
     PB_REQUIRE(Bt <= 65535 && ceil_div(N, BN) <= 65535, "pw_gemm_simt: grid too large");
     dim3 grid(ceil_div(R, BM), ceil_div(N, BN), Bt);
     PB_DISPATCH_DTYPE(dtype, {
-        (void)launch_pdl(gemm_simt_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)A, W, w_sn, w_sk, bias, ascale, colscale, coladd, (T*)C, R, K, N);
+        (void)launch_pdl(gemm_simt_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)A, W, w_sn,
+                         w_sk, bias, ascale, colscale, coladd, (T*)C, R, K, N);
     });
     PB_CHECK_LAUNCH("gemm_simt_kernel");
     return PB_OK;
@@ -232,7 +233,8 @@ extern "C" int pb_pw_wgrad_simt(const void* A, const void* dC, const float* asca
     rows = (rows + BK - 1) / BK * BK;
     dim3 grid(ceil_div(M, rows), ceil_div(N, BN), ceil_div(K, BM));
     PB_DISPATCH_DTYPE(dtype, {
-        (void)launch_pdl(wgrad_simt_kernel<T>, dim3(grid), dim3(256), 0, st, (const T*)A, (const T*)dC, ascale, dW, dbias, M, R, K, N, rows);
+        (void)launch_pdl(wgrad_simt_kernel<T>, dim3(grid), dim3(256), 0, st, (const T*)A, (const T*)dC, ascale, dW,
+                         dbias, M, R, K, N, rows);
     });
     PB_CHECK_LAUNCH("wgrad_simt_kernel");
     return PB_OK;
@@ -244,11 +246,14 @@ extern "C" int pb_cast_matrix(const float* src, void* dst, int dst_dtype, int ro
     long long n = (long long)rows * cols;
     cudaStream_t st = (cudaStream_t)stream;
     if (dst_dtype == PB_BF16)
-        (void)launch_pdl(cast_matrix_kernel<__nv_bfloat16>, dim3(ceil_div(n, 256)), dim3(256), 0, st, src, (__nv_bfloat16*)dst, rows, cols, transpose, 0);
+        (void)launch_pdl(cast_matrix_kernel<__nv_bfloat16>, dim3(ceil_div(n, 256)), dim3(256), 0, st, src,
+                         (__nv_bfloat16*)dst, rows, cols, transpose, 0);
     else if (dst_dtype == PB_F32)
-        (void)launch_pdl(cast_matrix_kernel<float>, dim3(ceil_div(n, 256)), dim3(256), 0, st, src, (float*)dst, rows, cols, transpose, 0);
+        (void)launch_pdl(cast_matrix_kernel<float>, dim3(ceil_div(n, 256)), dim3(256), 0, st, src, (float*)dst, rows,
+                         cols, transpose, 0);
     else if (dst_dtype == PB_F32_RBF16)   // fp32 storage, values rounded through bf16 (autocast's weight cast)
-        (void)launch_pdl(cast_matrix_kernel<float>, dim3(ceil_div(n, 256)), dim3(256), 0, st, src, (float*)dst, rows, cols, transpose, 1);
+        (void)launch_pdl(cast_matrix_kernel<float>, dim3(ceil_div(n, 256)), dim3(256), 0, st, src, (float*)dst, rows,
+                         cols, transpose, 1);
     else { set_error("cast_matrix: bad dst dtype %d", dst_dtype); return PB_ERR_BAD_ARG; }
     PB_CHECK_LAUNCH("cast_matrix_kernel");
     return PB_OK;
@@ -260,7 +265,8 @@ extern "C" int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, i
     PB_REQUIRE(((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(gate) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0,
                "fold_gate: pointers must be 16-byte aligned");
     long long n = (long long)Bt * N * (K / 8);
-    (void)launch_pdl(fold_gate_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, W, gate, (__nv_bfloat16*)dst, N, K, n);
+    (void)launch_pdl(fold_gate_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, W, gate,
+                     (__nv_bfloat16*)dst, N, K, n);
     PB_CHECK_LAUNCH("fold_gate_kernel");
     return PB_OK;
 }

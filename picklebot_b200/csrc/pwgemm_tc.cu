@@ -438,11 +438,14 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = (int)std::min<long long>(p.total_tiles, sms);
     if (bias || colscale || coladd)
-        PB_CUDA(launch_pdl(gemm_tc_kernel<true, false>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
+        PB_CUDA(launch_pdl(gemm_tc_kernel<true, false>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW,
+                           p));
     else if (stats)
-        PB_CUDA(launch_pdl(gemm_tc_kernel<false, true>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
+        PB_CUDA(launch_pdl(gemm_tc_kernel<false, true>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW,
+                           p));
     else
-        PB_CUDA(launch_pdl(gemm_tc_kernel<false, false>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW, p));
+        PB_CUDA(launch_pdl(gemm_tc_kernel<false, false>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW,
+                           p));
     PB_CHECK_LAUNCH("gemm_tc_kernel");
     return PB_OK;
 }

@@ -202,10 +202,12 @@ extern "C" int pb_se_fc_fwd(const float* mean, const float* W1, const float* b1,
     PB_REQUIRE(C <= FC_MAX_K && Ch <= FC_MAX_K, "se_fc_fwd: channel count too large for the shared-memory staging");
     if (int e = fc_smem_attrs()) return e;
     dim3 g1(ceil_div(Ch, 32), ceil_div(B, FC_BT));
-    (void)launch_pdl(fc_rows_kernel<PB_ACT_RELU>, dim3(g1), dim3(256), sizeof(float) * FC_BT * C, st, mean, W1, b1, hidden, B, Ch, C);
+    (void)launch_pdl(fc_rows_kernel<PB_ACT_RELU>, dim3(g1), dim3(256), sizeof(float) * FC_BT * C, st, mean, W1, b1,
+                     hidden, B, Ch, C);
     PB_CHECK_LAUNCH("se_fc_fwd(1)");
     dim3 g2(ceil_div(C, 32), ceil_div(B, FC_BT));
-    (void)launch_pdl(fc_rows_kernel<PB_ACT_HSIGMOID>, dim3(g2), dim3(256), sizeof(float) * FC_BT * Ch, st, hidden, W2, b2, gate, B, C, Ch);
+    (void)launch_pdl(fc_rows_kernel<PB_ACT_HSIGMOID>, dim3(g2), dim3(256), sizeof(float) * FC_BT * Ch, st, hidden, W2,
+                     b2, gate, B, C, Ch);
     PB_CHECK_LAUNCH("se_fc_fwd(2)");
     return PB_OK;
 }
@@ -229,14 +231,17 @@ extern "C" int pb_se_fc_bwd(const float* dgate, const float* mean, const float* 
                "se_fc_bwd: channel count too large for the shared-memory staging");
     if (int e = fc_smem_attrs()) return e;
     const size_t red_bytes = sizeof(float) * 8 * FC_BT * 33;
-    (void)launch_pdl(fc_cols_kernel, dim3(g1), dim3(256), sizeof(float) * FC_BT * C + red_bytes, st, a2, W2, hidden, a1, B, Ch, C, 1.f);
+    (void)launch_pdl(fc_cols_kernel, dim3(g1), dim3(256), sizeof(float) * FC_BT * C + red_bytes, st, a2, W2, hidden,
+                     a1, B, Ch, C, 1.f);
     PB_CHECK_LAUNCH("se_fc_bwd(da1)");
     // dmean[b][c] = inv_R * sum_j da1[b][j] * W1[j][c]         (W1 is [Ch][C] = "Wt" with K=Ch, N=C)
     dim3 g2(ceil_div(C, 32), ceil_div(B, FC_BT));
-    (void)launch_pdl(fc_cols_kernel, dim3(g2), dim3(256), sizeof(float) * FC_BT * Ch + red_bytes, st, a1, W1, nullptr, dmean, B, C, Ch, inv_R);
+    (void)launch_pdl(fc_cols_kernel, dim3(g2), dim3(256), sizeof(float) * FC_BT * Ch + red_bytes, st, a1, W1, nullptr,
+                     dmean, B, C, Ch, inv_R);
     PB_CHECK_LAUNCH("se_fc_bwd(dmean)");
     long long n = 2LL * C * Ch + C + Ch;
-    (void)launch_pdl(se_fc_bwd_param_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, a2, a1, mean, hidden, dW1, db1, dW2, db2, B, C, Ch);
+    (void)launch_pdl(se_fc_bwd_param_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, a2, a1, mean, hidden, dW1, db1,
+                     dW2, db2, B, C, Ch);
     PB_CHECK_LAUNCH("se_fc_bwd(param)");
     return PB_OK;
 }

@@ -59,7 +59,8 @@ extern "C" int pb_pool_fwd(const void* x, int dtype, int B, long long R, int C, 
     dim3 grid = colreduce_grid(R, C, B);
     PB_DISPATCH_DTYPE(dtype, {
         PoolF<T> f{(const T*)x, R, C};
-        (void)launch_pdl(colreduce_kernel<PoolF<T>, 1, float>, dim3(grid), dim3(256), 0, st, f, R, C, mean, B, 1.f / (float)R);
+        (void)launch_pdl(colreduce_kernel<PoolF<T>, 1, float>, dim3(grid), dim3(256), 0, st, f, R, C, mean, B,
+                         1.f / (float)R);
     });
     PB_CHECK_LAUNCH("pool_fwd");
     return PB_OK;
@@ -84,7 +85,8 @@ extern "C" int pb_rowscale(const void* x, const float* gate, void* y, int dtype,
     PB_REQUIRE(x && gate && y && B > 0 && R > 0 && C > 0 && C % 8 == 0, "rowscale: bad args");
     long long total = (long long)B * R * (C / 8);
     PB_DISPATCH_DTYPE(dtype, {
-        (void)launch_pdl(rowscale_kernel<T, false>, dim3(ceil_div(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const T*)x, gate, nullptr, (T*)y, R, C, total);
+        (void)launch_pdl(rowscale_kernel<T, false>, dim3(ceil_div(total, 256)), dim3(256), 0, (cudaStream_t)stream,
+                         (const T*)x, gate, nullptr, (T*)y, R, C, total);
     });
     PB_CHECK_LAUNCH("rowscale");
     return PB_OK;
@@ -95,7 +97,8 @@ extern "C" int pb_scale_add(void* g, const float* gate, const float* add, int dt
     PB_REQUIRE(g && gate && add && B > 0 && R > 0 && C > 0 && C % 8 == 0, "scale_add: bad args");
     long long total = (long long)B * R * (C / 8);
     PB_DISPATCH_DTYPE(dtype, {
-        (void)launch_pdl(rowscale_kernel<T, true>, dim3(ceil_div(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const T*)g, gate, add, (T*)g, R, C, total);
+        (void)launch_pdl(rowscale_kernel<T, true>, dim3(ceil_div(total, 256)), dim3(256), 0, (cudaStream_t)stream,
+                         (const T*)g, gate, add, (T*)g, R, C, total);
     });
     PB_CHECK_LAUNCH("scale_add");
     return PB_OK;
