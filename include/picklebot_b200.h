@@ -129,11 +129,13 @@ int pb_block_diag_bf16(const void* W, void* dst, int F, int N, int K, pb_stream_
 #define PB_STAT_REPLICAS 16
 /* sums[r][0][c] = partial sum_m x, sums[r][1][c] = partial sum_m x^2 (fp64, overwritten). */
 int pb_colstats(const void* x, int dtype, long long M, int C, double* sums, pb_stream_t stream);
-/* training: mean/var from sums, running stats updated (momentum, unbiased var), else running stats.
+/* training: mean/var from sums, running stats updated (momentum, unbiased var), num_batches_tracked (int64
+ * device scalar, may be NULL) incremented; else running stats.
  * Writes scale = gamma*invstd, shift = beta - mean*scale, mean, invstd (all [C]). */
 int pb_bn_finalize(const double* sums, long long M, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, int training, float momentum, float eps,
-                   float* scale, float* shift, float* mean, float* invstd, int C, pb_stream_t stream);
+                   float* scale, float* shift, float* mean, float* invstd, long long* num_batches_tracked,
+                   int C, pb_stream_t stream);
 /* out = act(z*scale + shift) * mask[b][c]   (mask NULL = no dropout; mask holds 0 or 1/(1-p)). */
 int pb_bn_act_fwd(const void* z, const float* scale, const float* shift, const float* mask, void* out,
                   int dtype, int B, long long R, int C, int act, float slope, pb_stream_t stream);

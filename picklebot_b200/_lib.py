@@ -34,7 +34,7 @@ SIGNATURES = {
     "pb_fold_gate_bf16": "pppiiip",
     "pb_block_diag_bf16": "ppiiip",
     "pb_colstats": "pilipp",
-    "pb_bn_finalize": "plppppiffppppip",
+    "pb_bn_finalize": "plppppiffpppppip",
     "pb_bn_act_fwd": "pppppiiliifp",
     "pb_bn_act_bwd_reduce": "pippppppp" + "iiliifp",
     "pb_bn_bwd_finalize": "plipppip",

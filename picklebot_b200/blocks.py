@@ -195,9 +195,7 @@ def bn_forward(z: torch.Tensor, B: int, C: int, gamma, beta, rmean, rvar, nbt, t
     elif sums is None:
         sums = ops.colstats(z, C)
     scale, shift, mean, invstd = ops.bn_finalize(sums, M, gamma, beta, rmean, rvar, use_batch, momentum, eps, C,
-                                                 z.device)
-    if use_batch and nbt is not None:
-        nbt.add_(1)
+                                                 z.device, nbt=nbt if use_batch else None)
     out = ops.bn_act_fwd(z, scale, shift, mask, B, C, act, slope)
     return out, (scale, shift, mean, invstd)
 

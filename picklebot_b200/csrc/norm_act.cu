@@ -25,10 +25,12 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double M, co
                                    const float* __restrict__ beta, float* __restrict__ rmean,
                                    float* __restrict__ rvar, int training, float momentum, float eps,
                                    float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_o, float* __restrict__ invstd_o, int C) {
+                                   float* __restrict__ mean_o, float* __restrict__ invstd_o,
+                                   long long* __restrict__ nbt, int C) {
     pdl_trigger();
     pdl_wait();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt && training) *nbt += 1;           // nn.BatchNorm's num_batches_tracked
     if (c >= C) return;
     float mean, var;
     if (training) {
@@ -307,11 +309,13 @@ extern "C" int pb_colstats(const void* x, int dtype, long long M, int C, double*
 
 extern "C" int pb_bn_finalize(const double* sums, long long M, const float* gamma, const float* beta,
                               float* running_mean, float* running_var, int training, float momentum, float eps,
-                              float* scale, float* shift, float* mean, float* invstd, int C, pb_stream_t stream) {
+                              float* scale, float* shift, float* mean, float* invstd,
+                              long long* num_batches_tracked, int C, pb_stream_t stream) {
     PB_REQUIRE(scale && shift && C > 0, "bn_finalize: bad args");
     PB_REQUIRE(training ? (sums != nullptr && M > 0) : (running_mean && running_var), "bn_finalize: missing statistics");
     (void)launch_pdl(bn_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, (double)M,
-                     gamma, beta, running_mean, running_var, training, momentum, eps, scale, shift, mean, invstd, C);
+                     gamma, beta, running_mean, running_var, training, momentum, eps, scale, shift, mean, invstd,
+                     num_batches_tracked, C);
     PB_CHECK_LAUNCH("bn_finalize");
     return PB_OK;
 }

@@ -213,10 +213,13 @@ def colstats(x: torch.Tensor, C: int) -> torch.Tensor:
 
 
 def bn_finalize(sums, M: int, gamma, beta, rmean, rvar, training: bool, momentum: float, eps: float, C: int,
-                device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+                device, nbt=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """nbt: nn.BatchNorm's num_batches_tracked (int64 device scalar), incremented by the kernel when training."""
     out = torch.empty((4, C), dtype=torch.float32, device=device)
+    if nbt is not None:
+        assert nbt.dtype == torch.int64 and nbt.is_cuda
     call("pb_bn_finalize", _p(sums), M, _p(gamma), _p(beta), _p(rmean), _p(rvar), int(training), momentum, eps,
-         out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), C, _st())
+         out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), _p(nbt), C, _st())
     return out[0], out[1], out[2], out[3]
 
 

@@ -42,7 +42,7 @@ def _run_eager(m, opt, batches, autocast):
 @pytest.mark.parametrize("model,autocast", [("MobileNetLarge3D", False), ("MobileNetSmall3D", False), ("MoViNetA2", False),
                                             ("MobileNetLarge3D", True), ("MoViNetA2", True)])
 def test_graphed_step_matches_eager(model, autocast, monkeypatch):
-    """Two optimizer steps of three accumulated micro-batches: replayed graph vs eager on a twin model.
+    """Two passes of three accumulated micro-batches, the weights rescaled in between: replayed graph vs eager twin.
     fp32 storage: 1e-4 (only the order of atomic partial sums differs).  bf16 autocast: the kernels' atomics make
     even two eager runs differ, and at this tiny batch a single flipped bf16 rounding moves the loss by ~1e-2 (two
     eager twins are printed for reference), so the bf16 bar is a sanity bound, the fp32 one is the proof."""
@@ -74,20 +74,25 @@ def test_graphed_step_matches_eager(model, autocast, monkeypatch):
         g_g = torch.cat([p.grad.flatten() for p in m_g.parameters()])
         noise_l = max(abs(a - b) for a, b in zip(l_e, l_e2))
         noise_g = rel_err(g_e2, g_e)
-        print(f"\n{model} step {it}: eager-vs-eager loss {noise_l:.2e} grads {noise_g:.2e}; graph-vs-eager loss "
-              f"{max(abs(a - b) for a, b in zip(l_e, l_g)):.2e} grads {rel_err(g_g, g_e):.2e}")
         d_l, d_g = max(abs(a - b) for a, b in zip(l_e, l_g)), rel_err(g_g, g_e)
+        print(f"\n{model} pass {it}: eager-vs-eager loss {noise_l:.2e} grads {noise_g:.2e}; graph-vs-eager loss "
+              f"{d_l:.2e} grads {d_g:.2e}")
         if autocast:
             assert d_l <= max(3 * noise_l, 3e-2) and d_g <= max(3 * noise_g, 0.3)
-        elif it == 0:
-            # the proof: same arithmetic, only the atomics reorder partial sums (MoViNetA2's 26 train-mode BN layers
-            # over <= 128 samples amplify that most; the eager twins bound it)
-            assert noise_g < 2e-3 and d_l <= 2e-4 and d_g <= max(3 * noise_g, 2e-4)
         else:
-            # after an SGD step the two trajectories amplify that round-off alike (see the eager twins)
-            assert d_l <= max(3 * noise_l, 1e-4) and d_g <= max(3 * noise_g, 2e-4)
-        for o in opts:
-            o.step()
+            # the proof: same arithmetic, only the atomics reorder partial sums (the eager twins bound that)
+            assert d_l <= max(3 * noise_l, 2e-4) and d_g <= max(3 * noise_g, 2e-4)
+        if it == 0:
+            # change the weights the way an optimizer does (in place, bumping the version): the replayed graph must
+            # follow, i.e. re-cast its bf16 / transposed / block-diagonal shadow copies
+            first_losses = l_g
+            with torch.no_grad():
+                for m in (m_e, m_e2, m_g):
+                    for p in m.parameters():
+                        if p.dim() > 1:
+                            p.mul_(0.9)
+        else:
+            assert max(abs(a - b) for a, b in zip(first_losses, l_g)) > 10 * max(d_l, 1e-4)    # it did follow
     sd_e, sd_g = m_e.state_dict(), m_g.state_dict()
     for k in sd_e:
         if k.endswith("num_batches_tracked"):
