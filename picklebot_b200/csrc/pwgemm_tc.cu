@@ -48,6 +48,7 @@ struct GemmParams {
     int Bt, K, N, Bw;
     long long R;
     int block_n, n_tiles, m_tiles, k_chunks, stages, mt;
+    int w_resident;    // the whole weight matrix stays in shared memory for the CTA's lifetime (see pb_pw_gemm_tc)
     int bk;            // K elements per chunk = swizzle span / 2: 64 (128B), 32 (64B) or 16 (32B rows) for tiny K
     long long total_tiles;
     const float* bias;
@@ -70,7 +71,7 @@ template <bool EPI, bool STATS>   // EPI: any of bias / colscale / coladd presen
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2], wres_bar;
     __shared__ uint32_t tmem_base_s;
     pdl_trigger();
 
@@ -81,7 +82,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int A_SUB_BYTES = BM * pitch;                                 // one 128-row sub-tile
     const uint32_t layout = pitch == 128 ? 2u : pitch == 64 ? 4u : 6u;  // UMMA layout type of the swizzle mode
     const int a_stage_bytes = p.mt * A_SUB_BYTES;
-    const int stage_bytes = a_stage_bytes + p.block_n * pitch;
+    const int w_bytes = p.block_n * pitch;                              // one K-chunk of the weight tile
+    const int stage_bytes = a_stage_bytes + (p.w_resident ? 0 : w_bytes);
+    uint8_t* wres = tiles + (size_t)p.stages * stage_bytes;             // resident weights: [k_chunks][block_n][pitch]
+    const int wres_bytes = p.w_resident ? p.k_chunks * w_bytes : 0;
     const int acc_cols = p.mt * p.block_n;                              // TMEM columns per accumulator stage
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -90,6 +94,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmW);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+        mbar_init(&wres_bar, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(&tmem_base_s, TMEM_COLS);
@@ -102,6 +107,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
+            if (p.w_resident) {                 // one weight tile for every row tile: fetch it once
+                mbar_expect_tx(&wres_bar, (uint32_t)wres_bytes);
+                for (int kc = 0; kc < p.k_chunks; ++kc)
+                    tma_load_3d(wres + (size_t)kc * w_bytes, &tmW, &wres_bar, kc * BK, 0, 0);
+            }
             for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const int n_tile = (int)(t % p.n_tiles);
                 const long long mtile = t / p.n_tiles;
@@ -112,7 +122,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* st = tiles + (size_t)s * stage_bytes;
                     for (int sub = 0; sub < p.mt; ++sub)
                         tma_load_3d(st + sub * A_SUB_BYTES, &tmA, &full_bar[s], kc * BK, (m_tile * p.mt + sub) * BM, b);
-                    tma_load_3d(st + a_stage_bytes, &tmW, &full_bar[s], kc * BK, n_tile * p.block_n, p.Bw == 1 ? 0 : b);
+                    if (!p.w_resident)
+                        tma_load_3d(st + a_stage_bytes, &tmW, &full_bar[s], kc * BK, n_tile * p.block_n, p.Bw == 1 ? 0 : b);
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -122,6 +133,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t idesc = make_idesc(BM, p.block_n, 0, 0);
             int s = 0; uint32_t ph = 0;
             long long it = 0;
+            if (p.w_resident) {
+                mbar_wait(&wres_bar, 0);
+                tc_fence_after();
+            }
             for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
                 const int a = (int)(it & 1);
                 const uint32_t aph = (uint32_t)((it >> 1) & 1);
@@ -132,7 +147,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint64_t bdesc = make_desc(sa + a_stage_bytes, 16, 8 * pitch, layout);
+                    const uint64_t bdesc = make_desc(p.w_resident ? smem_u32(wres) + (uint32_t)(kc * w_bytes) : sa + a_stage_bytes,
+                                                     16, 8 * pitch, layout);
                     for (int sub = 0; sub < p.mt; ++sub) {
                         const uint64_t adesc = make_desc(sa + sub * A_SUB_BYTES, 16, 8 * pitch, layout);
                         for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes = 2 descriptor units
@@ -150,7 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // tile, so the TMEM loads / conversions / stores of consecutive tiles overlap
         const int q = warp & 3;
         const int group = (warp - 4) >> 2;
-        uint8_t* stage_w = tiles + (size_t)p.stages * stage_bytes + (size_t)(warp - 4) * EPI_STAGE_BYTES;
+        uint8_t* stage_w = wres + wres_bytes + (size_t)(warp - 4) * EPI_STAGE_BYTES;
         // STATS: after the staging transpose a lane owns 8 fixed columns of each 64-column panel, so the
         // BatchNorm sums of the rounded outputs accumulate in registers over every tile of this CTA
         float st_sum[STATS ? 4 : 1][8], st_sq[STATS ? 4 : 1][8];
@@ -398,8 +414,13 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     }
     p.m_tiles = ceil_div(R, (long long)BM * p.mt);
     p.total_tiles = (long long)Bt * p.m_tiles * p.n_tiles;
-    const int stage_bytes = (p.mt * BM + p.block_n) * BK * 2;
-    p.stages = std::min(MAX_STAGES, RING_BYTES / stage_bytes);
+    // One weight tile serves every row tile when N fits one tile and the weights are shared by all samples: keep it
+    // resident instead of re-fetching block_n TMA rows per row tile (for 40 -> 240 channels that was two thirds of
+    // all box rows the TMA unit processed).
+    const int wres_bytes = p.k_chunks * p.block_n * BK * 2;
+    p.w_resident = (Bw == 1 && p.n_tiles == 1 && wres_bytes <= 64 * 1024) ? 1 : 0;
+    const int stage_bytes = p.w_resident ? p.mt * BM * BK * 2 : (p.mt * BM + p.block_n) * BK * 2;
+    p.stages = std::min(MAX_STAGES, (RING_BYTES - (p.w_resident ? wres_bytes : 0)) / stage_bytes);
     PB_REQUIRE(p.stages >= 2, "pw_gemm_tc: internal tiling error");
     p.bias = bias; p.colscale = colscale; p.coladd = coladd; p.C = (__nv_bfloat16*)C;
     p.stats = stats; p.stat_mod = stat_mod;
@@ -408,7 +429,7 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
         PB_REQUIRE(stat_mod > 0 && N % stat_mod == 0, "pw_gemm_tc: stat_mod=%d must divide N=%d", stat_mod, N);
         PB_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * PB_STAT_REPLICAS * 2 * stat_mod, (cudaStream_t)stream));
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + 8 * EPI_STAGE_BYTES + 1024;
+    const size_t smem = (size_t)p.stages * stage_bytes + (p.w_resident ? wres_bytes : 0) + 8 * EPI_STAGE_BYTES + 1024;
 
     CUtensorMap tmA, tmW;
     {
