@@ -9,8 +9,8 @@ current stream (tensor maps are encoded on the host and baked into the kernel pa
 keep their addresses -- torch's graph memory pool guarantees that), the Dropout3d noise comes from torch's
 graph-aware Philox generator, BatchNorm running statistics and ``num_batches_tracked`` are updated in place.
 
-Gradients: every parameter gets a persistent ``.grad`` BEFORE capture, so the captured backward accumulates
-into it in place (``grad += ...``), which makes replays compose with gradient accumulation; the caller zeroes the
+Gradients: every parameter gets a persistent ``.grad`` BEFORE capture and the captured backward adds into it in
+place (one multi-tensor add), which makes replays compose with gradient accumulation; the caller zeroes the
 gradients at the start of an optimizer step (``GradientBuckets.zero_grad()`` or ``optimizer.zero_grad(
 set_to_none=False)`` -- never ``set_to_none=True``, the graph holds the addresses).  Hooks do not fire on replay:
 under data parallelism capture inside ``GradientBuckets.no_sync()`` and exchange with ``reduce_all()`` +
@@ -48,6 +48,7 @@ class GraphedTrainStep:
         for p in model.parameters():
             if p.requires_grad and p.grad is None:
                 p.grad = torch.zeros_like(p)
+        self._params = [p for p in model.parameters() if p.requires_grad]
         # the warm-up passes are real training passes: put the BatchNorm running statistics back afterwards
         buffers = [(b, b.detach().clone()) for b in model.buffers()]
         # warm-up on a side stream (torch.cuda.graph's rule): lazy one-time initialisation happens here
@@ -81,7 +82,11 @@ class GraphedTrainStep:
                 loss = self.loss_fn(self.model(self.x), self.y)
         else:
             loss = self.loss_fn(self.model(self.x), self.y)
-        loss.backward()
+        # gradients are taken with autograd.grad and added to .grad with one multi-tensor kernel: loss.backward()
+        # would launch one small accumulation kernel per parameter (~170 for MobileNetLarge3D)
+        grads = torch.autograd.grad(loss, self._params, allow_unused=True)
+        pairs = [(p.grad, g) for p, g in zip(self._params, grads) if g is not None]
+        torch._foreach_add_([a for a, _ in pairs], [g if g.dtype == a.dtype else g.to(a.dtype) for a, g in pairs])
         return loss.detach()
 
     def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
