@@ -5,6 +5,8 @@
 // and their backward.  Two kernel shapes cover everything:
 //   fc_rows: W stored [N][K] (outputs are rows): one warp per output, lanes stride over K, BT samples per CTA
 //   fc_cols: W stored [K][N] (outputs are columns): one thread per output, sequential over K
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace pb {
@@ -116,36 +118,68 @@ __global__ void hsig_bwd_kernel(const float* __restrict__ dgate, const float* __
     da2[i] = (g > 0.f && g < 1.f) ? dgate[i] * (1.f / 6.f) : 0.f;
 }
 
-// parameter gradients: sums over the B samples
-__global__ void se_fc_bwd_param_kernel(const float* __restrict__ a2, const float* __restrict__ a1,
-                                       const float* __restrict__ mean, const float* __restrict__ hidden,
-                                       float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
-                                       float* __restrict__ db2, int B, int C, int Ch) {
+// Parameter gradients: outer products summed over the B samples,
+//   dW2[c][j] = sum_b da2[b][c] * hidden[b][j]   db2[c] = sum_b da2[b][c]       (blockIdx.z == 0)
+//   dW1[j][c] = sum_b da1[b][j] * mean[b][c]     db1[j] = sum_b da1[b][j]       (blockIdx.z == 1)
+// i.e. out[r][c] = sum_b X[b][r] * Y[b][c] twice.  A CTA owns a 64 x 64 tile of `out`: the samples' X and Y
+// columns are staged 32 samples at a time in shared memory, a thread keeps a 4 x 4 register tile (two LDS.128 per
+// 16 FMAs); the row sums (bias gradients) come from the threads of the first column of tiles.
+__global__ void __launch_bounds__(256)
+se_fc_bwd_param_kernel(const float* __restrict__ a2, const float* __restrict__ a1,
+                       const float* __restrict__ mean, const float* __restrict__ hidden,
+                       float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
+                       float* __restrict__ db2, int B, int C, int Ch) {
     pdl_trigger();
     pdl_wait();
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long nW = (long long)C * Ch;
-    if (idx < nW) {                       // dW2[c][j] = sum_b da2[b][c] * hidden[b][j]
-        int c = (int)(idx / Ch), j = (int)(idx % Ch);
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s = fmaf(a2[(long long)b * C + c], hidden[(long long)b * Ch + j], s);
-        dW2[idx] = s;
-    } else if (idx < 2 * nW) {            // dW1[j][c] = sum_b da1[b][j] * mean[b][c]
-        long long i = idx - nW;
-        int j = (int)(i / C), c = (int)(i % C);
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s = fmaf(a1[(long long)b * Ch + j], mean[(long long)b * C + c], s);
-        dW1[i] = s;
-    } else if (idx < 2 * nW + C) {
-        int c = (int)(idx - 2 * nW);
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s += a2[(long long)b * C + c];
-        db2[c] = s;
-    } else if (idx < 2 * nW + C + Ch) {
-        int j = (int)(idx - 2 * nW - C);
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s += a1[(long long)b * Ch + j];
-        db1[j] = s;
+    constexpr int BC = 32;
+    __shared__ __align__(16) float xs[BC][64], ys[BC][64];
+    const bool second = blockIdx.z == 1;
+    const float* X = second ? a1 : a2;
+    const float* Y = second ? mean : hidden;
+    const int Rn = second ? Ch : C, Cn = second ? C : Ch;
+    float* out = second ? dW1 : dW2;
+    float* rowsum = second ? db1 : db2;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    if (r0 >= Rn || c0 >= Cn) return;
+    const int tr = threadIdx.x >> 4, tc = threadIdx.x & 15;
+    float acc[4][4], rs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        rs[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    }
+    for (int b0 = 0; b0 < B; b0 += BC) {
+        for (int e = threadIdx.x; e < BC * 64; e += 256) {
+            const int bi = e >> 6, k = e & 63, b = b0 + bi;
+            xs[bi][k] = (b < B && r0 + k < Rn) ? __ldg(X + (long long)b * Rn + r0 + k) : 0.f;
+            ys[bi][k] = (b < B && c0 + k < Cn) ? __ldg(Y + (long long)b * Cn + c0 + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int bi = 0; bi < BC; ++bi) {
+            const float4 xv = *reinterpret_cast<const float4*>(&xs[bi][tr * 4]);
+            const float4 yv = *reinterpret_cast<const float4*>(&ys[bi][tc * 4]);
+            const float x[4] = {xv.x, xv.y, xv.z, xv.w}, y[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                rs[i] += x[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x[i], y[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + tr * 4 + i;
+        if (r >= Rn) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + tc * 4 + j;
+            if (c < Cn) out[(long long)r * Cn + c] = acc[i][j];
+        }
+        if (blockIdx.x == 0 && tc == 0) rowsum[r] = rs[i];
     }
 }
 
@@ -239,8 +273,8 @@ extern "C" int pb_se_fc_bwd(const float* dgate, const float* mean, const float* 
     (void)launch_pdl(fc_cols_kernel, dim3(g2), dim3(256), sizeof(float) * FC_BT * Ch + red_bytes, st, a1, W1, nullptr,
                      dmean, B, C, Ch, inv_R);
     PB_CHECK_LAUNCH("se_fc_bwd(dmean)");
-    long long n = 2LL * C * Ch + C + Ch;
-    (void)launch_pdl(se_fc_bwd_param_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, a2, a1, mean, hidden, dW1, db1,
+    const int big = std::max(C, Ch);
+    (void)launch_pdl(se_fc_bwd_param_kernel, dim3(ceil_div(big, 64), ceil_div(big, 64), 2), dim3(256), 0, st, a2, a1, mean, hidden, dW1, db1,
                      dW2, db2, B, C, Ch);
     PB_CHECK_LAUNCH("se_fc_bwd(param)");
     return PB_OK;
