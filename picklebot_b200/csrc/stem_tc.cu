@@ -86,21 +86,35 @@ __device__ __forceinline__ void gather_row(const TX* __restrict__ x, const StemT
     uint32_t cur[4];
     float prev = 0.f;
     const bool all_interior = __all_sync(0xffffffffu, interior);
-    if (StcLoad<TX>::IS_U8 && all_interior) {
-        // uint8 clip: the 9 bytes of a patch row come from three aligned 32-bit loads (27 loads per pixel instead of
-        // 81 byte loads); byte -> float exactly through the 2^23 mantissa trick, then the same * (1/255) as the
-        // scalar path, so both paths produce identical bf16 values.  The last word read may extend up to 3 bytes
-        // past the patch row but never past the 4-byte word holding the clip's last byte.
+    // uint8 clip, word path: taken unless a lane's patch sticks out on the RIGHT (kw = 1 or 2 invalid: reading the
+    // 9 bytes could then run past the clip's end).  Left padding (w0 = -1), padded rows / frames and the invalid
+    // pixels of a partial tile are handled by masks, so the ~30 % of warps that touch a border do not fall back to
+    // 81 byte loads + I2F per pixel.
+    const bool word_ok = !valid || (colmask & 6u) == 6u;
+    if (StcLoad<TX>::IS_U8 && __all_sync(0xffffffffu, word_ok)) {
+        // The 9 bytes of a patch row come from three aligned 32-bit loads; byte -> float exactly through the 2^23
+        // mantissa trick, then the same * (1/255) as the scalar path, so both paths produce identical bf16 values.
+        // The last word read may extend up to 3 bytes past the patch row but never past the 4-byte word holding
+        // the clip's last byte.  With left padding the row is read from its first real pixel and shifted by 3 bytes.
+        const bool left_pad = valid && !(colmask & 1u);
+        const uint32_t m0 = left_pad ? 0xFF000000u : 0xFFFFFFFFu;          // bytes 0..2 belong to kw = 0
         uint32_t by[KT * 3][3];
 #pragma unroll
         for (int r = 0; r < KT * 3; ++r) {
-            const uintptr_t pa = reinterpret_cast<uintptr_t>(rowp[r]);
+            const uintptr_t pa = reinterpret_cast<uintptr_t>(rowp[r]) + (left_pad ? 3 : 0);
             const uint32_t* wp = reinterpret_cast<const uint32_t*>(pa & ~uintptr_t(3));
             const unsigned sh = (unsigned)(pa & 3) * 8;
             const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-            by[r][0] = __funnelshift_r(w0, w1, sh);
-            by[r][1] = __funnelshift_r(w1, w2, sh);
-            by[r][2] = w2 >> sh;
+            uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh), b2 = w2 >> sh;
+            if (left_pad) {                                    // shift the 9-byte string up by 3 bytes
+                b2 = b1 >> 8;
+                b1 = __funnelshift_l(b0, b1, 24);
+                b0 = b0 << 24;
+            }
+            const bool rok = (rowmask >> r) & 1u;
+            by[r][0] = rok ? (b0 & m0) : 0u;
+            by[r][1] = rok ? b1 : 0u;
+            by[r][2] = rok ? b2 : 0u;
         }
 #pragma unroll
         for (int k = 0; k < NCH * 8; ++k) {
@@ -109,7 +123,7 @@ __device__ __forceinline__ void gather_row(const TX* __restrict__ x, const StemT
                 const uint32_t m = __byte_perm(by[k / 9][(k % 9) >> 2], 0x4B000000u, 0x7540u + (uint32_t)((k % 9) & 3));
                 v = (__uint_as_float(m) - 8388608.f) * (1.0f / 255.0f);
             } else if (ONES && k == NK) {
-                v = 1.f;
+                v = valid ? 1.f : 0.f;
             }
             if (k & 1) cur[(k & 7) >> 1] = pack_bf16x2(prev, v); else prev = v;
             if ((k & 7) == 7) sts128(base + (uint32_t)(k >> 3) * 128, cur[0], cur[1], cur[2], cur[3]);
