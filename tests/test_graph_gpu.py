@@ -83,7 +83,10 @@ def test_graphed_step_matches_eager(model, autocast, monkeypatch):
         else:
             # the proof: same arithmetic, only the atomics reorder partial sums (the eager twins bound that;
             # MoViNetA2's 26 train-mode BN layers over <= 128 samples amplify it to the 1e-3 level)
-            floor_l, floor_g = (5e-4, 5e-3) if model == "MoViNetA2" else (2e-4, 2e-4)
+            # MobileNetLarge3D: with the synthetic checkpoint one block4.5 activation sits at u = 3.000000 +- 2e-6,
+            # the discontinuity of Hardswish' (1.5 -> 1.0, same in torch); the 1e-6 forward round-off decides on which
+            # side it falls, which moves the gradients by 0.7-1.2 % in about a third of all runs, eager or replayed.
+            floor_l, floor_g = {"MoViNetA2": (5e-4, 5e-3), "MobileNetLarge3D": (2e-4, 2e-2)}.get(model, (2e-4, 2e-4))
             assert d_l <= max(3 * noise_l, floor_l) and d_g <= max(3 * noise_g, floor_g)
         if it == 0:
             # change the weights the way an optimizer does (in place, bumping the version): the replayed graph must
