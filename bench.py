@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--profile-steps", type=int, default=1)
     ap.add_argument("--dp", default="buckets", choices=["buckets", "ddp"],
                     help="gradient exchange for N>1: picklebot_b200.dp.GradientBuckets or torch DDP")
+    ap.add_argument("--torch-optim", action="store_true",
+                    help="torch.optim.AdamW(fused=True) instead of picklebot_b200.optim.AdamW")
     ap.add_argument("--no-graphs", action="store_true",
                     help="issue every micro-batch eagerly instead of replaying picklebot_b200.graph.GraphedTrainStep")
     return ap.parse_args()
@@ -211,7 +213,11 @@ def main():
             from picklebot_b200 import dp as pbdp
             pbdp.broadcast_module(model)
             buckets = pbdp.GradientBuckets(model.parameters(), grad_as_bucket_view=True)
-    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=5e-4, fused=True)
+    if args.torch_optim:
+        opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=5e-4, fused=True)
+    else:
+        from picklebot_b200.optim import AdamW          # one pb_adamw_step launch over all ~170 tensors
+        opt = AdamW(model.parameters(), lr=3e-4, weight_decay=5e-4)
     use_graph = not args.no_graphs and args.dp == "buckets"
 
     # synthetic uint8 clips: this rank's shard of each global batch, distinct per micro-batch
@@ -420,7 +426,8 @@ def main():
                        "launch": ("forward+loss+backward of a micro-batch captured once in a CUDA graph "
                                   "(picklebot_b200.graph.GraphedTrainStep) and replayed; clips are copied device-to-"
                                   "device into the graph's static input" if gstep is not None else "eager"),
-                       "optimizer": "torch.optim.AdamW(fused=True) inside the timed region",
+                       "optimizer": ("torch.optim.AdamW(fused=True)" if args.torch_optim else
+                                     "picklebot_b200.optim.AdamW (multi-tensor pb_adamw_step)") + " inside the timed region",
                        "l2": "inputs larger than L2 (154 MB uint8 per micro-batch, distinct buffers); no flush",
                        "num_classes": NUM_CLASSES},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,

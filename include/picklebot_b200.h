@@ -196,6 +196,20 @@ int pb_stem_conv_wgrad(const void* x, int x_dtype, long long xs_b, long long xs_
                        int kT, int kH, int kW, int sT, int sH, int sW, int pT, int pH, int pW,
                        int To, int Ho, int Wo, pb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser step (train.py:208-212,283-289).  Multi-tensor AdamW with
+ * torch.optim.AdamW's arithmetic (decoupled weight decay, bias-corrected moments, fp32 state), one launch for
+ * all tensors.  Device tables: ptrs = [4][n_tensors] addresses (parameter, gradient, exp_avg, exp_avg_sq; all
+ * fp32), sizes[n_tensors] element counts, and a chunk list: CTA c updates elements [chunk_start[c],
+ * chunk_start[c] + pb_adamw_chunk_elems()) of tensor chunk_tensor[c].  bias_correction1 = 1 - beta1^t,
+ * bias_correction2_sqrt = sqrt(1 - beta2^t); gradients are multiplied by grad_scale first (1/loss-scale).
+ * ---------------------------------------------------------------------------------------------- */
+int pb_adamw_chunk_elems(void);
+int pb_adamw_step(const long long* ptrs, const long long* sizes, const int* chunk_tensor,
+                  const long long* chunk_start, int n_tensors, int n_chunks, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float bias_correction1, float bias_correction2_sqrt,
+                  float grad_scale, pb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

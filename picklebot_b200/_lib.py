@@ -49,9 +49,10 @@ SIGNATURES = {
     "pb_scale_add": "pppiilip",
     "pb_stem_conv_fwd": "pi" + "lllll" + "f" + "pppi" + "i" * 18 + "p",
     "pb_stem_conv_wgrad": "pi" + "lllll" + "f" + "pipp" + "i" * 18 + "p",
+    "pb_adamw_step": "pppp" + "ii" + "ffffffff" + "p",
 }
 PLAIN = ("pb_abi_version", "pb_last_error_string", "pb_launch_count", "pb_device_check",
-         "pb_pw_wgrad_tc_workspace_bytes")
+         "pb_pw_wgrad_tc_workspace_bytes", "pb_adamw_chunk_elems")
 EXPORTS = tuple(SIGNATURES) + PLAIN
 
 
@@ -75,6 +76,7 @@ def _load() -> ctypes.CDLL:
     lib.pb_device_check.restype = _I
     lib.pb_pw_wgrad_tc_workspace_bytes.argtypes = [_I, _L, _I, _I]
     lib.pb_pw_wgrad_tc_workspace_bytes.restype = _L
+    lib.pb_adamw_chunk_elems.restype = _I
     return lib
 
 
