@@ -219,6 +219,7 @@ def main():
         from picklebot_b200.optim import AdamW          # one pb_adamw_step launch over all ~170 tensors
         opt = AdamW(model.parameters(), lr=3e-4, weight_decay=5e-4)
     use_graph = not args.no_graphs and args.dp == "buckets"
+    from picklebot_b200 import loss as pbloss               # cross-entropy + accuracy count in one kernel (pb_ce_loss)
 
     # synthetic uint8 clips: this rank's shard of each global batch, distinct per micro-batch
     clips = [synth.synthetic_clips_u8_device(micro, *CLIP, seed=1000 * rank + a, device=dev) for a in range(accum)]
@@ -234,7 +235,7 @@ def main():
         from picklebot_b200.graph import GraphedTrainStep
         with (buckets.no_sync() if buckets is not None else nullcontext()):
             gstep = GraphedTrainStep(model, clips[0].permute(0, 4, 1, 2, 3), labels[0],
-                                     loss_fn=lambda logits, y: F.cross_entropy(logits.float(), y) / accum)
+                                     loss_fn=lambda logits, y: pbloss.cross_entropy(logits, y, scale=1.0 / accum))
         grad_list = [p.grad for p in model.parameters() if p.grad is not None]
 
     def zero_grads():
@@ -254,7 +255,7 @@ def main():
             return loss
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = net(x_u8.permute(0, 4, 1, 2, 3))        # (B,3,T,H,W) view of the uint8 NTHWC batch
-            loss = F.cross_entropy(logits.float(), y) / accum
+            loss = pbloss.cross_entropy(logits, y, scale=1.0 / accum)
         if world > 1 and not sync_grads:
             with (buckets.no_sync() if buckets is not None else net.no_sync()):
                 loss.backward()
@@ -426,6 +427,7 @@ def main():
                        "launch": ("forward+loss+backward of a micro-batch captured once in a CUDA graph "
                                   "(picklebot_b200.graph.GraphedTrainStep) and replayed; clips are copied device-to-"
                                   "device into the graph's static input" if gstep is not None else "eager"),
+                       "criterion": "picklebot_b200.loss.cross_entropy (pb_ce_loss), mean over the micro-batch / accum_steps",
                        "optimizer": ("torch.optim.AdamW(fused=True)" if args.torch_optim else
                                      "picklebot_b200.optim.AdamW (multi-tensor pb_adamw_step)") + " inside the timed region",
                        "l2": "inputs larger than L2 (154 MB uint8 per micro-batch, distinct buffers); no flush",

@@ -210,6 +210,15 @@ int pb_adamw_step(const long long* ptrs, const long long* sizes, const int* chun
                   float eps, float weight_decay, float bias_correction1, float bias_correction2_sqrt,
                   float grad_scale, pb_stream_t stream);
 
+/* Cross-entropy criterion + accuracy count (nn.CrossEntropyLoss, train.py:214,266-267; calculate_accuracy,
+ * train.py:110-114), fp32 logits [B][NC], int64 labels [B]:
+ *   loss[0]        = scale * mean_b (logsumexp(logits[b]) - logits[b][label_b])
+ *   dlogits[b][c]  = scale / B * (softmax(logits[b])[c] - [c == label_b])        (NULL to skip)
+ *   correct[0]     = #{b : argmax_c logits[b][c] == label_b}                     (int32 device scalar, NULL to skip)
+ * No host synchronisation: loss and count stay on the device. */
+int pb_ce_loss(const float* logits, const long long* labels, float* loss, float* dlogits, int* correct,
+               int B, int NC, float scale, pb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,7 @@ SIGNATURES = {
     "pb_stem_conv_fwd": "pi" + "lllll" + "f" + "pppi" + "i" * 18 + "p",
     "pb_stem_conv_wgrad": "pi" + "lllll" + "f" + "pipp" + "i" * 18 + "p",
     "pb_adamw_step": "pppp" + "ii" + "ffffffff" + "p",
+    "pb_ce_loss": "ppppp" + "iif" + "p",
 }
 PLAIN = ("pb_abi_version", "pb_last_error_string", "pb_launch_count", "pb_device_check",
          "pb_pw_wgrad_tc_workspace_bytes", "pb_adamw_chunk_elems")

@@ -63,3 +63,22 @@ def test_adamw_grad_scale_state_dict_and_errors():
     cpu[0].grad = torch.randn(4)
     with pytest.raises(RuntimeError):
         AdamW(cpu).step()
+
+
+@pytest.mark.parametrize("B,NC", [(64, 2), (7, 2), (33, 10), (4, 1000), (1, 3)])
+def test_cross_entropy_loss_gradient_and_accuracy(B, NC):
+    """pb_ce_loss against F.cross_entropy / argmax accuracy (train.py:110-114, 214, 266-267)."""
+    import torch.nn.functional as F
+    from picklebot_b200.loss import cross_entropy_with_accuracy
+    g = torch.Generator().manual_seed(B * 1000 + NC)
+    logits = (torch.randn(B, NC, generator=g) * 3).cuda().requires_grad_(True)
+    ref_logits = logits.detach().clone().requires_grad_(True)
+    labels = torch.randint(0, NC, (B,), generator=g).cuda()
+    loss, correct = cross_entropy_with_accuracy(logits, labels, scale=0.125)
+    ref = F.cross_entropy(ref_logits, labels) * 0.125
+    assert abs(float(loss) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    (loss * 3.0).backward()
+    (ref * 3.0).backward()
+    assert torch.allclose(logits.grad, ref_logits.grad, rtol=1e-5, atol=1e-8)
+    assert int(correct) == int((ref_logits.argmax(1) == labels).sum())
+    assert correct.dtype == torch.int32 and not correct.requires_grad
