@@ -11,16 +11,6 @@
 
 namespace pb {
 
-template <typename T>
-struct StatsF {
-    const T* x; long long R; int C;
-    __device__ void operator()(int b, long long r, int c0, float (&out)[2][8]) const {
-        F8 v = load8(x + ((long long)b * R + r) * C + c0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { out[0][i] = v.v[i]; out[1][i] = v.v[i] * v.v[i]; }
-    }
-};
-
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double M, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ rmean,
                                    float* __restrict__ rvar, int training, float momentum, float eps,

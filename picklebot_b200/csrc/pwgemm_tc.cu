@@ -59,14 +59,6 @@ struct GemmParams {
     int stat_mod;      // real channel count (column c of a row-folded problem is channel c % stat_mod)
 };
 
-__device__ __forceinline__ void ldg16(const float* p, float (&v)[16]) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + q);
-        v[q * 4 + 0] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
-    }
-}
-
 template <bool EPI, bool STATS>   // EPI: any of bias / colscale / coladd present; STATS: column sums of C
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmParams p) {
