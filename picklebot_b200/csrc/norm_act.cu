@@ -81,9 +81,7 @@ bn_act_fwd_kernel(const T* __restrict__ z, const float* __restrict__ scale, cons
     load_vec8(scale + L.c0, sc);
     load_vec8(shift + L.c0, sh);
     const unsigned stride = gridDim.x * L.RPI;
-    for (unsigned m = blockIdx.x * L.RPI + L.rr; m < M; m += stride) {
-        const size_t o = (size_t)m * C + L.c0;
-        F8 v = load8(z + o);
+    auto finish = [&](unsigned m, F8 v) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v.v[i] = actf<ACT>(fmaf(v.v[i], sc[i], sh[i]), slope);
         if (mask) {
@@ -92,8 +90,16 @@ bn_act_fwd_kernel(const T* __restrict__ z, const float* __restrict__ scale, cons
 #pragma unroll
             for (int i = 0; i < 8; ++i) v.v[i] *= mk[i];
         }
-        store8(out + o, v);
+        store8(out + (size_t)m * C + L.c0, v);
+    };
+    unsigned m = blockIdx.x * L.RPI + L.rr;
+    for (; m + stride < M; m += 2 * stride) {               // two rows in flight per thread
+        const F8 v0 = load8(z + (size_t)m * C + L.c0);
+        const F8 v1 = load8(z + (size_t)(m + stride) * C + L.c0);
+        finish(m, v0);
+        finish(m + stride, v1);
     }
+    if (m < M) finish(m, load8(z + (size_t)m * C + L.c0));
 }
 
 // du = dout * mask * act'(u), u = z*scale + shift, xhat = z*a + bb with a = invstd, bb = -mean*invstd
@@ -260,9 +266,12 @@ bn_bwd_apply_kernel(const void* __restrict__ dout, const T* __restrict__ z, cons
     }
 }
 
-static inline int row_grid(long long M, int C) {
+// rows_per_thread: 8 for the reductions (few atomics per CTA), 2 for the pure streaming kernels (small tensors
+// then still fill the machine)
+static inline int row_grid(long long M, int C, int rows_per_thread = 8) {
     int G = C >> 3, RPI = 256 / G;
-    long long max_ctas = (M + (long long)RPI * 8 - 1) / ((long long)RPI * 8);   // >= 8 rows per thread: few atomics
+    long long per_cta = (long long)RPI * rows_per_thread;
+    long long max_ctas = (M + per_cta - 1) / per_cta;
     long long want = 148LL * 8;
     return (int)std::max<long long>(1, std::min(max_ctas, want));
 }
@@ -315,7 +324,7 @@ extern "C" int pb_bn_act_fwd(const void* z, const float* scale, const float* shi
     PB_REQUIRE(z && scale && shift && out && B > 0 && R > 0 && C > 0 && C % 8 == 0 && C <= 2048, "bn_act_fwd: bad args");
     const long long M = (long long)B * R;
     PB_REQUIRE(M < (1LL << 31) && R < (1LL << 31), "bn_act_fwd: too many rows");
-    const int grid = row_grid(M, C);
+    const int grid = row_grid(M, C, 2);
     PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
         (void)launch_pdl(bn_act_fwd_kernel<T, ACT>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)z,
                          scale, shift, mask, (T*)out, (unsigned)M, (unsigned)R, C, slope);
@@ -365,7 +374,7 @@ extern "C" int pb_bn_act_bwd_apply(const void* dout, int dout_bcast, const void*
     PB_REQUIRE(B > 0 && R > 0 && C > 0 && C % 8 == 0 && C <= 2048, "bn_act_bwd_apply: bad dims");
     const long long M = (long long)B * R;
     PB_REQUIRE(M < (1LL << 31) && R < (1LL << 31), "bn_act_bwd_apply: too many rows");
-    const int grid = row_grid(M, C);
+    const int grid = row_grid(M, C, 2);
     cudaStream_t st = (cudaStream_t)stream;
     PB_DISPATCH_DTYPE(dtype, PB_DISPATCH_ACT(act, {
         if (dout_bcast)
