@@ -99,3 +99,18 @@ def test_product_never_imports_the_oracle():
                 ln for ln in src.splitlines() if "oracle" in ln and "import" in ln] or True
             for ln in src.splitlines():
                 assert not re.match(r"\s*(from|import)\s+oracle", ln), (fn, ln)
+
+
+def test_checkpoint_prefix_conversion_round_trip(tmp_path):
+    """Reference checkpoints saved from torch.compile / DDP wrappers (train.py:38-44,316-318,338) load strictly."""
+    import torch
+    import picklebot_b200 as pb
+    from picklebot_b200.checkpoint import load_reference_checkpoint, state_dict_converter
+    m = pb.MobileNetSmall3D(num_classes=2)
+    sd = {("module._orig_mod." if i % 2 else "_orig_mod.") + k: v.clone() for i, (k, v) in enumerate(m.state_dict().items())}
+    path = str(tmp_path / "ckpt.pth")
+    torch.save(sd, path)
+    m2 = load_reference_checkpoint(pb.MobileNetSmall3D(num_classes=2), path)
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    assert list(state_dict_converter({"a.b": 1, "_orig_mod.c": 2})) == ["a.b", "c"]
