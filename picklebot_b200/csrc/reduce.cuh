@@ -7,7 +7,7 @@
 
 namespace pb {
 
-constexpr int COLRED_UNROLL = 2;
+constexpr int COLRED_UNROLL = 4;
 
 // Fold the per-thread partials of one CTA over the row-slot index rr (threads tid and tid+h*G own the same
 // channels): a halving tree through shared memory (channel-major, so every access is conflict-free).  On
