@@ -555,7 +555,9 @@ static bool plan_tile(const PlanIn& in, DwTile& p) {
     auto src_extent = [&](int n) { return S == 0 ? n / 2 + (K - 1) / 2 + 1 : (n - 1) * S + K; };
     // Search (tiles_w, Ht): the tile must fit the per-stage budget; prefer the best ratio of useful
     // destination pixels to staged source pixels (halo efficiency), then the larger tile.
-    const int budget = 34 * 1024;                       // per stage; 3 stages x 2 CTAs fit in one SM
+    // per stage: 3 stages x 2 CTAs fit in one SM; the 5x5 kernels (issue-bound, wide halos) trade the third stage
+    // for larger tiles, i.e. less halo re-fetch
+    const int budget = (in.K == 5 ? 46 : 34) * 1024;
     const int hstep = (S == 0) ? 2 : 1;
     double best_score = -1.0;
     int best_ht = 0, best_wt = 0;
