@@ -5,8 +5,10 @@
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A "step" is one optimiser step over a global batch of 512 synthetic clips (3x16x224x224): every rank runs
-512/(64*N) micro-batches of 64 clips (forward under bf16 autocast, CrossEntropyLoss, backward, DDP's
-bucketed NCCL all-reduce overlapping backward when N>1), then one AdamW step.  Work per step is fixed, so
+512/(64*N) micro-batches of 64 clips (forward under bf16 autocast, cross-entropy, backward -- by default one
+replay of a CUDA graph captured by picklebot_b200.graph.GraphedTrainStep per micro-batch; --no-graphs issues the
+launches eagerly), the in-place NCCL all-reduce of the gradient buckets when N>1, then one multi-tensor AdamW
+step (picklebot_b200.optim.AdamW; --torch-optim for torch's fused one).  Work per step is fixed, so
 scaling is "strong"; the per-GPU micro-batch stays 64 so BatchNorm statistics do not depend on N
 (SURVEY.md section 8d, config 3).
 
