@@ -48,15 +48,44 @@ CLIP = (16, 224, 224)
 METRIC = "MobileNetLarge3D train clips/s"
 FALLBACK_HBM_GBS = 6650.0
 
+# BASELINE.json configs (1-based like the JSON list; configs[0] is the CPU golden case of the tests).  The driver's
+# plain `python bench.py` is config 3, the configuration the headline metric is quoted on; the others are run with
+# --config N and their lines are committed under profiles/.
+CONFIGS = {
+    2: dict(model="MobileNetLarge3D", mode="infer", clip=(16, 224, 224), micro=64, global_batch=512, nc=2,
+            metric="MobileNetLarge3D inference clips/s", scaling="strong",
+            workload="MobileNetLarge3D inference (eval mode), bf16 autocast, synthetic uint8 clips 3x16x224x224, batch 64 "
+                     "(BASELINE.json configs[1])"),
+    3: dict(model="MobileNetLarge3D", mode="train", clip=(16, 224, 224), micro=64, global_batch=512, nc=2,
+            metric=METRIC, scaling="strong",
+            workload="MobileNetLarge3D training step, bf16 autocast, synthetic uint8 clips 3x16x224x224 "
+                     "(BASELINE.json configs[2])"),
+    4: dict(model="MoViNetA2", mode="stream", clip=(64, 224, 224), chunk=8, micro=16, global_batch=16, nc=13,
+            metric="MoViNetA2 causal streaming inference clips/s (64-frame clips, 8-frame chunks)", scaling="weak",
+            workload="MoViNetA2 causal streaming inference, bf16, 64-frame 224x224 uint8 clips fed as 8 chunks of 8 frames, "
+                     "stream buffers and cumulative pooling state resident in HBM (BASELINE.json configs[3])"),
+    5: dict(model="MobileNetSmall3D", mode="train", clip=(32, 224, 224), micro=64, global_batch=512, nc=2,
+            metric="MobileNetSmall3D train clips/s (32-frame clips)", scaling="strong",
+            workload="MobileNetSmall3D training step, bf16 autocast, long synthetic uint8 clips 3x32x224x224 "
+                     "(BASELINE.json configs[4])"),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--micro", type=int, default=MICRO)
-    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-b200"])
+    ap.add_argument("--torch-mode", default="eager", choices=["eager", "compiled"],
+                    help="--impl torch-b200 only: the reference's torch ops eagerly or under torch.compile")
+    ap.add_argument("--no-torch-b200", action="store_true", help="skip the torch/cuDNN-on-this-B200 legs")
+    ap.add_argument("--torch-compile-budget", type=float, default=300.0,
+                    help="seconds the torch.compile(max-autotune-no-cudagraphs) leg may take before it is abandoned")
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS),
+                    help="BASELINE.json configuration (1-based); 3 = the headline MobileNetLarge3D training step")
+    ap.add_argument("--micro", type=int, default=None)
+    ap.add_argument("--global-batch", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=1)
@@ -66,7 +95,13 @@ def parse():
                     help="torch.optim.AdamW(fused=True) instead of picklebot_b200.optim.AdamW")
     ap.add_argument("--no-graphs", action="store_true",
                     help="issue every micro-batch eagerly instead of replaying picklebot_b200.graph.GraphedTrainStep")
-    return ap.parse_args()
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.micro is None:
+        args.micro = cfg["micro"]
+    if args.global_batch is None:
+        args.global_batch = cfg["global_batch"] * (args.gpus if cfg["scaling"] == "weak" else 1)
+    return args
 
 
 def peaks():
@@ -125,50 +160,163 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle's train step on the host cores
+# CPU arm: the oracle (restatement of the reference's torch ops) on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_train_clips_per_s(batch, reps, warm=1):
+def cpu_clips_per_s(cfg, batch, reps, warm=1):
+    """One 'step' of the configuration on the CPU, fp32: a training step (fwd+CE+bwd), an eval forward, or a
+    64-frame clip streamed in 8-frame chunks.  Returns (best, mean) clips/s and the individual times."""
     from oracle import picklebot_oracle as O          # bench's cpu_baseline / reference leg only
     import picklebot_b200 as pb
     from picklebot_b200 import synth
     torch.set_num_threads(os.cpu_count() or 1)
-    sd0 = synth.synthetic_state_dict(pb.MobileNetLarge3D(num_classes=NUM_CLASSES).state_dict())
-    clips = synth.synthetic_clips_u8(batch, *CLIP, seed=0)
+    model, nc = cfg["model"], cfg["nc"]
+    sd0 = synth.synthetic_state_dict(pb.valid_models[model](num_classes=nc).state_dict())
+    clips = synth.synthetic_clips_u8(batch, *cfg["clip"], seed=0)
     x = synth.clips_to_features(clips, torch.float32).contiguous()
-    labels = synth.synthetic_labels(batch, NUM_CLASSES)
+    labels = synth.synthetic_labels(batch, nc)
     times = []
     for i in range(warm + reps):
-        sd = O.clone_state(sd0, requires_grad=True)
         t0 = time.perf_counter()
-        torch.manual_seed(7)
-        O.train_step(MODEL, sd, x, labels)
+        if cfg["mode"] == "train":
+            sd = O.clone_state(sd0, requires_grad=True)
+            t0 = time.perf_counter()
+            torch.manual_seed(7)
+            O.train_step(model, sd, x, labels)
+        elif cfg["mode"] == "infer":
+            with torch.no_grad():
+                O.MODELS[model](sd0, x)
+        else:
+            ch = cfg["chunk"]
+            with torch.no_grad():
+                O.movinet_a2_stream(sd0, [x[:, :, t:t + ch].contiguous() for t in range(0, cfg["clip"][0], ch)])
         dt = time.perf_counter() - t0
         if i >= warm:
             times.append(dt)
     return batch / min(times), batch / (sum(times) / len(times)), times
 
 
+CPU_SAMPLE = {"train": "train steps (fwd+CE+bwd)", "infer": "eval forwards", "stream": "64-frame clips streamed in 8-frame chunks"}
+
+
+def cpu_batch(cfg):
+    return 1 if cfg["mode"] == "stream" else (2 if cfg["clip"][0] > 16 else 4)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
-    batch = 4
+    cfg = CONFIGS[args.config]
+    batch = cpu_batch(cfg)
     t0 = time.perf_counter()
-    best, mean, times = cpu_train_clips_per_s(batch, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
+    best, mean, times = cpu_clips_per_s(cfg, batch, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
     value = mean
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": cfg["metric"], "value": value, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * batch / value,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MobileNetLarge3D train step (fwd+CE+bwd), 3x16x224x224 clips, CPU fp32",
-                   "global_batch": args.global_batch, "micro_batch": batch, "clip": list(CLIP)},
+        "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["workload"] + " -- CPU fp32 arm", "global_batch": args.global_batch,
+                   "micro_batch": batch, "clip": list(cfg["clip"])},
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{len(times)} train steps of {batch} clips each (one step = a bounded sample "
-                                   f"of the {args.global_batch}-clip global batch); oracle = torch-op restatement "
+                         "sample": f"{len(times)} {CPU_SAMPLE[cfg['mode']]} of {batch} clips each (one step = a bounded "
+                                   f"sample of the {args.global_batch}-clip global batch); oracle = torch-op restatement "
                                    f"of the reference, which is pure Python and absent on the GPU box"},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# torch/cuDNN on this same B200: the reference's own GPU path (SURVEY section 8d "the real bar")
+# --------------------------------------------------------------------------------------------------
+def run_torch_b200(args):
+    """Child process (``--impl torch-b200``): the reference's ops (oracle restatement = the same ATen/cuDNN calls as
+    the reference modules) doing the same training step on cuda:LOCAL_RANK: micro-batches of 64 uint8 clips ->
+    ``permute/.to(bf16)/255`` (train.py:106) -> forward under autocast(bf16) -> CrossEntropyLoss -> backward
+    (train.py:264-269), fused AdamW per 512 clips; eager with cudnn.benchmark (train.py:193) or under
+    ``torch.compile(mode='max-autotune-no-cudagraphs')`` (train.py:181).  CUDA-event timed; prints one JSON line."""
+    from oracle import picklebot_oracle as O          # a measured BASELINE leg, like cpu_baseline; never the product
+    import picklebot_b200 as pb
+    from picklebot_b200 import synth
+    t_start = time.perf_counter()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.benchmark = True
+    cfg = CONFIGS[args.config]
+    train = cfg["mode"] == "train"
+    micro, accum = args.micro, args.global_batch // args.micro
+    sd = synth.synthetic_state_dict(pb.valid_models[cfg["model"]](num_classes=cfg["nc"]).state_dict())
+    sd = O.clone_state(sd, requires_grad=train, device=dev)
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.AdamW(params, lr=3e-4, weight_decay=5e-4, fused=True) if train else None
+    clips = [synth.synthetic_clips_u8_device(micro, *cfg["clip"], seed=a, device=dev) for a in range(2)]
+    labels = [synth.synthetic_labels(micro, cfg["nc"], seed=77 + a).to(dev) for a in range(2)]
+    fwd = O.MODELS[cfg["model"]]
+    if args.torch_mode == "compiled":
+        fwd = torch.compile(fwd, mode="max-autotune-no-cudagraphs")
+
+    def step():
+        for a in range(accum):
+            x = clips[a & 1].permute(0, 4, 1, 2, 3).to(torch.bfloat16) / 255            # train.py:106
+            if train:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss = F.cross_entropy(fwd(sd, x, True), labels[a & 1]) / accum
+                loss.backward()
+            else:
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):   # estimate_loss, train.py:123-153
+                    fwd(sd, x, False)
+        if train:
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+
+    step()                                    # warm-up: cudnn.benchmark autotuning / compilation happen here
+    torch.cuda.synchronize()
+    warm_s = time.perf_counter() - t_start
+    step()
+    steps = max(1, min(args.steps, 3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    print(json.dumps({"mode": args.torch_mode, "value": args.global_batch / (ms / 1000.0), "unit": "clips/s",
+                      "ms_per_step": ms, "steps": steps, "micro_batch": micro, "warmup_and_setup_s": warm_s,
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9, "torch": torch.__version__,
+                      "cudnn": torch.backends.cudnn.version()}), flush=True)
+
+
+def torch_b200_legs(args, local):
+    """Run the two torch legs as child processes of rank 0 (own CUDA context on the same GPU, which is idle while the
+    parent waits) so that a slow torch.compile cannot wedge the bench: the compiled leg gets a wall-clock budget."""
+    out = {}
+    for mode, budget in (("eager", 240.0), ("compiled", args.torch_compile_budget)):
+        if budget <= 0:
+            out[mode] = {"unavailable": "disabled (budget 0)"}
+            continue
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "torch-b200", "--torch-mode", mode, "--steps",
+               str(args.steps), "--micro", str(args.micro), "--global-batch", str(args.global_batch),
+               "--config", str(args.config)]
+        env = dict(os.environ, LOCAL_RANK=str(local))
+        for k in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        t0 = time.perf_counter()
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=budget, env=env)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and line:
+                out[mode] = json.loads(line[-1])
+            else:
+                out[mode] = {"unavailable": f"exit {r.returncode}: " + (r.stderr.strip().splitlines() or ["?"])[-1][:300]}
+        except subprocess.TimeoutExpired:
+            out[mode] = {"unavailable": f"not finished within the {budget:.0f} s budget (--torch-compile-budget)"}
+        out[mode]["wall_s"] = time.perf_counter() - t0
+    out["what"] = ("the reference's torch ops (ATen/cuDNN) on this same B200: uint8 clips -> .to(bf16)/255 -> autocast(bf16) "
+                   "forward + CE + backward at micro-batch 64, fused AdamW per 512 clips; eager with cudnn.benchmark "
+                   "(train.py:193,264-269) and torch.compile(mode='max-autotune-no-cudagraphs') (train.py:181)")
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -181,6 +329,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "torch-b200":
+        run_torch_b200(args)
         return
     import torch.distributed as dist
     import picklebot_b200 as pb
@@ -241,10 +392,10 @@ def main():
         grad_list = [p.grad for p in model.parameters() if p.grad is not None]
 
     def zero_grads():
-        if gstep is None:
-            opt.zero_grad(set_to_none=True)
-        elif buckets is not None:
+        if buckets is not None:
             buckets.zero_grad()                 # one fill per bucket; .grad tensors are views of the buckets
+        elif gstep is None:
+            opt.zero_grad(set_to_none=True)
         else:
             torch._foreach_zero_(grad_list)     # the graph accumulates into these very tensors
 
@@ -411,6 +562,14 @@ def main():
                "sample": f"{len(times)} train steps (fwd+CE+bwd) of 4 clips 3x16x224x224, fp32, oracle "
                          f"(torch-op restatement of the reference) on the host cores"}
 
+    torch_b200 = None
+    if rank == 0 and world == 1 and not args.no_torch_b200:
+        torch.cuda.empty_cache()
+        torch_b200 = torch_b200_legs(args, local)
+        for mode in ("eager", "compiled"):
+            if "value" in torch_b200.get(mode, {}):
+                torch_b200[mode]["ours_over_torch"] = value / torch_b200[mode]["value"]
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
@@ -435,7 +594,7 @@ def main():
                        "l2": "inputs larger than L2 (154 MB uint8 per micro-batch, distinct buffers); no flush",
                        "num_classes": NUM_CLASSES},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "kernels": kernels,
+            "cpu_baseline": cpu, "torch_b200": torch_b200, "kernels": kernels,
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

@@ -39,6 +39,16 @@ const char* pb_last_error_string(void);
 long long   pb_launch_count(void);      /* kernels launched by this library since load (all threads) */
 int         pb_device_check(void);      /* PB_OK iff the current device is sm_100 (B200) */
 
+/* Which kernel family served a call: every entry point that can pick between a Blackwell fast path
+ * (TMA-staged tiles / tcgen05) and a CUDA-core correctness path counts the choice here, so tests can assert
+ * that the production path ran instead of inferring it from timings.  Counters are process-wide. */
+enum { PB_PATH_DW_FWD_TMA = 0, PB_PATH_DW_FWD_GENERIC, PB_PATH_DW_DGRAD_TMA, PB_PATH_DW_DGRAD_GENERIC,
+       PB_PATH_DW_WGRAD_TMA, PB_PATH_DW_WGRAD_GENERIC, PB_PATH_GEMM_TC, PB_PATH_GEMM_SIMT,
+       PB_PATH_WGRAD_TC, PB_PATH_WGRAD_SIMT, PB_PATH_STEM_TC, PB_PATH_STEM_SIMT,
+       PB_PATH_DW_BWD_FUSED_TMA, PB_PATH_DW_STREAM_TMA, PB_PATH_DW_STREAM_GENERIC, PB_PATH_COUNT };
+long long   pb_path_count(int path);    /* calls served by `path` since load / the last reset; -1 if out of range */
+void        pb_path_reset(void);
+
 /* ------------------------------------------------------------------------------------------------
  * Depthwise Conv3d, groups == C.  Replaces Bottleneck3D.depthwise_conv (mobilenet.py:67-75,86: kernel
  * (1,k,k) with SCALAR stride/padding, so time is padded and strided too) and MoviNetBottleneck.conv
@@ -215,6 +225,8 @@ int pb_adamw_step(const long long* ptrs, const long long* sizes, const int* chun
  *   loss[0]        = scale * mean_b (logsumexp(logits[b]) - logits[b][label_b])
  *   dlogits[b][c]  = scale / B * (softmax(logits[b])[c] - [c == label_b])        (NULL to skip)
  *   correct[0]     = #{b : argmax_c logits[b][c] == label_b}                     (int32 device scalar, NULL to skip)
+ * Samples whose label lies outside [0, NC) (e.g. torch's ignore_index -100) are skipped and B above becomes the
+ * number of remaining samples, as nn.CrossEntropyLoss(reduction="mean") does for ignored targets.
  * No host synchronisation: loss and count stay on the device. */
 int pb_ce_loss(const float* logits, const long long* labels, float* loss, float* dlogits, int* correct,
                int B, int NC, float scale, pb_stream_t stream);

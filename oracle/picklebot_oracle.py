@@ -137,6 +137,16 @@ def _mobilenet_stem(sd: SD, x: torch.Tensor, train: bool, momentum) -> torch.Ten
     return F.hardswish(x)
 
 
+def mobilenet_large_tail(sd: SD, x: torch.Tensor, train: bool, momentum: Optional[float] = 0.1) -> torch.Tensor:
+    """block6 + classifier of MobileNetLarge3D (mobilenet.py:178-190, 199-200) on a block5 output."""
+    x = F.conv3d(x, sd["block6.0.weight"], sd["block6.0.bias"])
+    x = F.hardswish(_bn(sd, "block6.1.", x, train, momentum))
+    x = F.adaptive_avg_pool3d(x, 1)
+    x = F.hardswish(F.conv3d(x, sd["classifier.1.weight"], sd["classifier.1.bias"]))
+    x = F.conv3d(x, sd["classifier.3.weight"], sd["classifier.3.bias"])
+    return x.view(x.shape[0], -1)
+
+
 def mobilenet_large3d(sd: SD, x: torch.Tensor, train: bool = False, masks: Optional[list] = None,
                       momentum: Optional[float] = 0.1, taps: Optional[dict] = None) -> torch.Tensor:
     """MobileNetLarge3D.forward, mobilenet.py:192-201.  ``taps`` (optional dict) receives the

@@ -53,7 +53,11 @@ SIGNATURES = {
     "pb_ce_loss": "ppppp" + "iif" + "p",
 }
 PLAIN = ("pb_abi_version", "pb_last_error_string", "pb_launch_count", "pb_device_check",
-         "pb_pw_wgrad_tc_workspace_bytes", "pb_adamw_chunk_elems")
+         "pb_pw_wgrad_tc_workspace_bytes", "pb_adamw_chunk_elems", "pb_path_count", "pb_path_reset")
+# PB_PATH_* of include/picklebot_b200.h, in enum order
+PATHS = ("dw_fwd_tma", "dw_fwd_generic", "dw_dgrad_tma", "dw_dgrad_generic", "dw_wgrad_tma", "dw_wgrad_generic",
+         "gemm_tc", "gemm_simt", "wgrad_tc", "wgrad_simt", "stem_tc", "stem_simt", "dw_bwd_fused_tma",
+         "dw_stream_tma", "dw_stream_generic")
 EXPORTS = tuple(SIGNATURES) + PLAIN
 
 
@@ -78,6 +82,10 @@ def _load() -> ctypes.CDLL:
     lib.pb_pw_wgrad_tc_workspace_bytes.argtypes = [_I, _L, _I, _I]
     lib.pb_pw_wgrad_tc_workspace_bytes.restype = _L
     lib.pb_adamw_chunk_elems.restype = _I
+    lib.pb_path_count.argtypes = [_I]
+    lib.pb_path_count.restype = _L
+    lib.pb_path_reset.argtypes = []
+    lib.pb_path_reset.restype = None
     return lib
 
 
@@ -132,3 +140,13 @@ def call(name: str, *args, nbytes: int = 0, tag: str = "") -> None:
 
 def launch_count() -> int:
     return int(lib().pb_launch_count())
+
+
+def path_counts() -> dict:
+    """Calls served by each kernel family since load / the last ``path_reset()`` (``PATHS`` names):
+    tests use it to assert that the TMA / tcgen05 production kernels ran, not the CUDA-core correctness paths."""
+    return {name: int(lib().pb_path_count(i)) for i, name in enumerate(PATHS)}
+
+
+def path_reset() -> None:
+    lib().pb_path_reset()

@@ -373,16 +373,18 @@ class MoViNetTailFn(torch.autograd.Function):
         Cmid = wc.shape[0]
         R = T * H * W
         hs = ACT_CODES["hswish"]
+        # (BatchNorm3d, BatchNorm1d) each with its own mode, eps and momentum (movinet.py:141,150)
+        (training, training1), (eps, eps1), (momentum, momentum1) = training, eps, momentum
         z = pw_fwd(x5.view(-1, Cin), wc, cache, "tail_conv")
         a, bn_state = bn_forward(z, B, Cmid, gamma.detach(), beta.detach(), rmean, rvar, nbt, training, eps, momentum,
                                  hs, 0.0, mask3d)
         feat = ops.pool_fwd(a, B, Cmid)
         F1, NC = wf1.shape[0], wf2.shape[0]
         u1 = ops.fc_fwd(feat, wf1.detach(), bf1.detach())
-        h1, bn1_state = bn_forward(u1, B, F1, gamma1.detach(), beta1.detach(), rmean1, rvar1, nbt1, training, eps,
-                                   momentum, hs, 0.0, mask1d)
+        h1, bn1_state = bn_forward(u1, B, F1, gamma1.detach(), beta1.detach(), rmean1, rvar1, nbt1, training1, eps1,
+                                   momentum1, hs, 0.0, mask1d)
         logits = ops.fc_fwd(h1, wf2.detach(), bf2.detach())
-        ctx.cache, ctx.training = cache, training
+        ctx.cache, ctx.training, ctx.training1 = cache, training, training1
         ctx.shapes = (B, T, H, W, Cin, Cmid, R, F1, NC)
         ctx.save_for_backward(x5, z, mask3d, mask1d, *bn_state, feat, u1, *bn1_state, h1, wc, wf1, wf2)
         return logits
@@ -398,7 +400,7 @@ class MoViNetTailFn(torch.autograd.Function):
         dwf2, dbf2 = ops.wgrad_simt(h1, dl, F1, NC, want_bias=True)
         dh1 = ops.fc_dgrad(dl, wf2.detach())
         du1, dgamma1, dbeta1 = ops.bn_act_bwd(dh1, False, u1, scale1, shift1, mean1, invstd1, mask1d, B, F1, hs,
-                                              ctx.training)
+                                              ctx.training1)
         dwf1, dbf1 = ops.wgrad_simt(feat, du1, Cmid, F1, want_bias=True)
         dfeat = ops.fc_dgrad(du1, wf1.detach(), 1.0 / R)
         dz, dgamma, dbeta = ops.bn_act_bwd(dfeat, True, z, scale, shift, mean, invstd, mask3d, B, Cmid, hs,

@@ -16,7 +16,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libpicklebot_b200.so")
 OBJ = os.path.join(HERE, "_build")
-SOURCES = ["runtime.cu", "dwconv.cu", "dwconv_tiled.cu", "pwgemm_simt.cu", "pwgemm_tc.cu", "pwwgrad_tc.cu", "norm_act.cu",
+SOURCES = ["runtime.cu", "dwconv.cu", "dwconv_tiled.cu", "dwconv_mma.cu", "pwgemm_simt.cu", "pwgemm_tc.cu", "pwwgrad_tc.cu", "norm_act.cu",
            "se_pool.cu", "se_fc.cu", "stem.cu", "stem_tc.cu", "optim.cu", "loss.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -19,6 +19,7 @@ namespace pb {
 void set_error(const char* fmt, ...);
 int  cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
+void count_path(int path);
 
 #define PB_REQUIRE(cond, ...)                                   \
     do {                                                        \
@@ -75,6 +76,19 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember which devices of this process
+// already have it (bit d of `done`), so a second GPU used by the same process is configured too.
+template <typename KernelT>
+static inline cudaError_t ensure_dyn_smem(KernelT kernel, int bytes, unsigned long long* done) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(done, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) __atomic_fetch_or(done, bit, __ATOMIC_RELEASE);
+    return e;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -210,11 +210,12 @@ extern "C" int pb_dwconv3d_fwd(const void* x, const float* w_tc, void* y, int dt
     if (int e = check_dims(d)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     PB_DISPATCH_DTYPE(dtype, {
-        if (dw_fwd_tiled<T>((const T*)x, w_tc, (T*)y, d, st)) { PB_CHECK_LAUNCH("dw_fwd_tiled"); return PB_OK; }
+        if (dw_fwd_tiled<T>((const T*)x, w_tc, (T*)y, d, st)) { PB_CHECK_LAUNCH("dw_fwd_tiled"); count_path(PB_PATH_DW_FWD_TMA); return PB_OK; }
         long long total = (long long)B * To * Ho * Wo * (C / 8);
         dw_fwd_generic<T, false><<<ceil_div(total, 256), 256, 0, st>>>((const T*)x, nullptr, w_tc, (T*)y, d, total);
     });
     PB_CHECK_LAUNCH("dw_fwd_generic");
+    count_path(PB_PATH_DW_FWD_GENERIC);
     return PB_OK;
 }
 
@@ -223,11 +224,12 @@ extern "C" int pb_dwconv3d_dgrad(const void* dy, const float* w_tc, void* dx, in
     if (int e = check_dims(d)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     PB_DISPATCH_DTYPE(dtype, {
-        if (dw_dgrad_tiled<T>((const T*)dy, w_tc, (T*)dx, d, st)) { PB_CHECK_LAUNCH("dw_dgrad_tiled"); return PB_OK; }
+        if (dw_dgrad_tiled<T>((const T*)dy, w_tc, (T*)dx, d, st)) { PB_CHECK_LAUNCH("dw_dgrad_tiled"); count_path(PB_PATH_DW_DGRAD_TMA); return PB_OK; }
         long long total = (long long)B * T_ * H * W * (C / 8);
         dw_dgrad_generic<T><<<ceil_div(total, 256), 256, 0, st>>>((const T*)dy, w_tc, (T*)dx, d, total);
     });
     PB_CHECK_LAUNCH("dw_dgrad_generic");
+    count_path(PB_PATH_DW_DGRAD_GENERIC);
     return PB_OK;
 }
 
@@ -239,7 +241,7 @@ extern "C" int pb_dwconv3d_wgrad(const void* x, const void* dy, float* dw_tc, in
     const int taps = kT * kH * kW;
     PB_CUDA(cudaMemsetAsync(dw_tc, 0, sizeof(float) * (size_t)taps * C, st));
     PB_DISPATCH_DTYPE(dtype, {
-        if (dw_wgrad_tiled<T>((const T*)x, (const T*)dy, dw_tc, d, st)) { PB_CHECK_LAUNCH("dw_wgrad_tiled"); return PB_OK; }
+        if (dw_wgrad_tiled<T>((const T*)x, (const T*)dy, dw_tc, d, st)) { PB_CHECK_LAUNCH("dw_wgrad_tiled"); count_path(PB_PATH_DW_WGRAD_TMA); return PB_OK; }
         long long P = (long long)B * To * Ho * Wo;
         int G = C / 8, RPI = 256 / G;
         int gx = (int)std::min<long long>(ceil_div(P, RPI), 148 * 8);
@@ -247,6 +249,7 @@ extern "C" int pb_dwconv3d_wgrad(const void* x, const void* dy, float* dw_tc, in
         dw_wgrad_generic<T><<<grid, 256, sizeof(float) * TAPC * C, st>>>((const T*)x, (const T*)dy, dw_tc, d, P);
     });
     PB_CHECK_LAUNCH("dw_wgrad_generic");
+    count_path(PB_PATH_DW_WGRAD_GENERIC);
     return PB_OK;
 }
 
@@ -264,6 +267,7 @@ extern "C" int pb_stream_dwconv3d_fwd(const void* x, const void* stream_buf, con
         long long total = (long long)B * T_ * Ho * Wo * (C / 8);
         dw_fwd_generic<T, true><<<ceil_div(total, 256), 256, 0, st>>>((const T*)x, (const T*)stream_buf, w_tc, (T*)y, d, total);
         PB_CHECK_LAUNCH("dw_fwd_stream");
+        count_path(PB_PATH_DW_STREAM_GENERIC);
         if (kT > 1) {
             long long fe8 = (long long)H * W * (C / 8);
             long long n = (long long)B * (kT - 1) * fe8;

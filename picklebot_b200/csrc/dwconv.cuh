@@ -16,4 +16,8 @@ template <typename T> bool dw_fwd_tiled(const T* x, const float* w_tc, T* y, con
 template <typename T> bool dw_dgrad_tiled(const T* dy, const float* w_tc, T* dx, const DwDims& d, cudaStream_t st);
 template <typename T> bool dw_wgrad_tiled(const T* x, const T* dy, float* dw_tc, const DwDims& d, cudaStream_t st);
 
+// Tensor-core (mma.sync) stride-1 kernels of dwconv_mma.cu; same contract (false = not handled).
+bool dw_fwd_mma(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y, const DwDims& d, cudaStream_t st);
+bool dw_dgrad_mma(const __nv_bfloat16* dy, const float* w_tc, __nv_bfloat16* dx, const DwDims& d, cudaStream_t st);
+
 }  // namespace pb

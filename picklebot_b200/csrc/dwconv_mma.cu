@@ -1,0 +1,426 @@
+// Depthwise (1,k,k) convolution, stride 1, bf16 NDHWC: TMA-staged halo tiles in, warp-level tensor-core FMAs,
+// TMA-stored output tiles out.
+//
+// Why tensor cores for an HBM-bound stencil: the CUDA-core kernels of dwconv_tiled.cu need ~20 (3x3) to ~30 (5x5)
+// issued instructions per output element -- bf16->fp32 unpacking, address arithmetic and 25 FMAs per element of a
+// 5x5 filter -- which caps them at 2-3.5 TB/s with the issue slots half busy (ncu, profiles/r01_ncu_dw_*); a 5x5
+// stride-1 layer at 70 % of the HBM rate would need 77 % of the chip's fp32 FMA peak.  tcgen05.mma cannot take
+// this problem: its operands must be canonical shared-memory / TMEM tiles, and a depthwise filter shares no operand
+// between channels, so with channels-last data every K-step would be strided by the channel count.  The legacy
+// warp-level mma.sync takes its operands from REGISTERS, which lets each lane assemble exactly the fragment it
+// needs from the staged tile:
+//
+//   per channel c and filter row i:   D[m][n] += sum_k A[m][k] * B_i[k][n]            (m16n8k16, bf16 -> fp32)
+//     A[m][k]   = tile[row(m) + i][wbase(m) + k][c]        16 contexts (row, 16-pixel window) x 16 input columns
+//     B_i[k][n] = w[i][k - n]  (0 <= k-n < K, else 0)      the filter row as a banded (Toeplitz) matrix
+//     D[m][n]   = output pixel wbase(m) + n of context m
+//
+// A window is NCH chunks of 16 input columns and yields 16*NCH - (K-1) outputs; output columns 8..15 of a chunk
+// reuse the same B registers shifted by 8 ({0,b0} / {b1,0}), so a lane holds 2 weight registers per (channel, i).
+// A lane owns contexts g and g+8 (g = lane/4), two consecutive destination rows.  Fragments are built from 8-byte
+// shared-memory loads (4 channels of one pixel) with one PRMT per register (pixel pair of one channel): ~0.5 ALU
+// instructions per staged element and filter row instead of ~1 per tap.  Products are exact and accumulate in
+// fp32, like the CUDA-core kernels.  Instruction budget: ~5 (3x3) / ~9 (5x5) per output element.
+//
+// Output: lanes hold (pixel, 4 channels) fragments, i.e. 8-byte pieces 2*C bytes apart -- written straight to
+// global memory that would be one 32-byte sector per lane.  They are staged in a shared-memory output tile
+// [NF][Ht][Wt][Cb] instead and one thread issues a cp.async.bulk.tensor store (the TMA unit clips ragged edges),
+// double buffered so the store of tile n overlaps the math of tile n+1.
+//
+// Used for: forward of the stride-1 Bottleneck3D.depthwise_conv layers (mobilenet.py:67-75) and their input
+// gradient (same kernel, flipped taps, roles of x and y swapped).
+#include <algorithm>
+#include <cstdlib>
+
+#include "dwconv.cuh"
+#include "tc_common.cuh"
+
+namespace pb {
+
+using namespace tc;
+
+constexpr int DWM_CWARPS = 8;                       // compute warps
+constexpr int DWM_COMPUTE = DWM_CWARPS * 32;
+constexpr int DWM_THREADS = DWM_COMPUTE + 32;       // + one warp that drives the TMA unit (loads and stores)
+constexpr int DWM_MAX_STAGES = 4;
+constexpr int DWM_MAX_ZF = 64;
+constexpr int DWM_SMEM_BUDGET = 216 * 1024;
+
+struct MmaPlan {
+    int B, C;
+    int To, Ho, Wo;             // destination tensor
+    int p;                      // spatial padding
+    int Cb, NCG, nblk;          // channel block, 4-channel groups per block, blocks
+    int NW, VW, RP;             // windows per tile row, outputs per window, destination rows per pass
+    int Ht, Hi, Wi, NF;         // tile: NF frames x Ht x Wo outputs, staged NF x Hi x Wi (full width)
+    int NP;                     // passes per tile = ceil(NF*Ht / RP)
+    int tiles_h, tiles_f;
+    int f_first, f_count, src_first;   // destination frames with a source frame (contiguous), and the first source frame
+    int nzf;
+    unsigned char zf[DWM_MAX_ZF];
+    long long ntiles;
+    int in_bytes, stages, tab_bytes;
+    int flip;
+};
+
+struct MmaCtx {
+    uint64_t full[DWM_MAX_STAGES];      // TMA load of the stage has landed
+    uint64_t done[DWM_MAX_STAGES];      // all compute warps have finished the tile (outputs written in place)
+};
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2,
+                                         const uint32_t a3, const uint32_t b0, const uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// Plain C++ accesses to the dynamic shared-memory array: the compiler is free to schedule them around the MMAs
+// (software pipelining of the next row's loads), while the "memory" clobbers of the mbarrier waits and the block
+// barrier keep them on the right side of the synchronisation points.
+__device__ __forceinline__ uint2 lds64m(const uint8_t* p) { return *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ uint4 lds128m(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void sts64m(uint8_t* p, uint32_t x, uint32_t y) { *reinterpret_cast<uint2*>(p) = make_uint2(x, y); }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// A-fragment halves of one tile row: for chunk q and channel c, lo = pixels (2t, 2t+1), hi = pixels (2t+8, 2t+9)
+template <int NCH>
+struct RowFrag {
+    uint32_t lo[NCH][4];
+    uint32_t hi[NCH][4];
+};
+
+template <int NCH>
+__device__ __forceinline__ void load_row(RowFrag<NCH>& f, const uint8_t* addr, uint32_t pb) {
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) {
+        const uint8_t* a = addr + (uint32_t)(16 * q) * pb;
+        const uint2 l0 = lds64m(a), l1 = lds64m(a + pb), l8 = lds64m(a + 8 * pb), l9 = lds64m(a + 9 * pb);
+        f.lo[q][0] = prmt(l0.x, l1.x, 0x5410); f.lo[q][1] = prmt(l0.x, l1.x, 0x7632);
+        f.lo[q][2] = prmt(l0.y, l1.y, 0x5410); f.lo[q][3] = prmt(l0.y, l1.y, 0x7632);
+        f.hi[q][0] = prmt(l8.x, l9.x, 0x5410); f.hi[q][1] = prmt(l8.x, l9.x, 0x7632);
+        f.hi[q][2] = prmt(l8.y, l9.y, 0x5410); f.hi[q][3] = prmt(l8.y, l9.y, 0x7632);
+    }
+}
+
+template <int K, int NCH>
+__global__ void __launch_bounds__(DWM_THREADS, 1)
+dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                 const float* __restrict__ w_tc, __nv_bfloat16* __restrict__ y, const MmaPlan p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ MmaCtx cx;
+    constexpr int NT = 2 * NCH;                          // 8-wide output column groups per window
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* ring = smem_raw + (((raw + 127u) & ~127u) - raw);
+    uint8_t* tab = ring + (size_t)p.stages * p.in_bytes;
+    const int tid = threadIdx.x;
+    const int c_base = blockIdx.y * p.Cb;
+    const uint32_t pb = (uint32_t)p.Cb * 2;              // bytes per staged pixel
+    pdl_trigger();
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&cx.full[s], 1); mbar_init(&cx.done[s], DWM_CWARPS); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmY);
+    }
+    pdl_wait();                 // w_tc (a cast kernel's output) and the activations are valid from here on
+    // weight table: tab[cg][i][slot][4 ch] = packed (w[i][slot-1], w[i][slot]) as bf16 pairs, zero outside the filter
+    {
+        uint32_t* t32 = reinterpret_cast<uint32_t*>(tab);
+        const int n = p.NCG * K * 8 * 4;
+        for (int e = tid; e < n; e += DWM_THREADS) {
+            const int ch = e & 3, slot = (e >> 2) & 7, i = (e >> 5) % K, cg = (e >> 5) / K;
+            const int c = c_base + cg * 4 + ch;
+            float lo = 0.f, hi = 0.f;
+            if (c < p.C) {
+                const int d0 = slot - 1, d1 = slot;
+                if (d0 >= 0 && d0 < K) { const int tap = i * K + d0; lo = w_tc[(long long)(p.flip ? K * K - 1 - tap : tap) * p.C + c]; }
+                if (d1 >= 0 && d1 < K) { const int tap = i * K + d1; hi = w_tc[(long long)(p.flip ? K * K - 1 - tap : tap) * p.C + c]; }
+            }
+            t32[e] = pack_bf16x2(lo, hi);
+        }
+    }
+    __syncthreads();
+    const int my_tiles = p.ntiles > blockIdx.x ? (int)((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+    if (tid >= DWM_COMPUTE) {
+        // ---- TMA warp: one lane.  Loads fill the ring; when the compute warps are done with a tile (its outputs
+        // now sit in the stage, at the positions of the top-left input pixels) the tile is stored from there and,
+        // once the store has read the stage, the stage is refilled with the tile `stages` ahead.
+        if (tid == DWM_COMPUTE) {
+            auto tile_coord = [&](int n) {
+                unsigned t = (unsigned)blockIdx.x + (unsigned)n * gridDim.x;      // ntiles < 2^31 (checked on the host)
+                int3 c;
+                c.z = (int)(t % p.tiles_h) * p.Ht; t /= p.tiles_h;
+                c.y = (int)(t % p.tiles_f);
+                c.x = (int)(t / p.tiles_f);
+                return c;
+            };
+            auto issue_load = [&](int n) {
+                const int s = n % p.stages;
+                const int3 c = tile_coord(n);
+                mbar_expect_tx(&cx.full[s], (uint32_t)(p.NF * p.Hi * p.Wi * p.Cb * 2));
+                tma_load_5d(ring + (size_t)s * p.in_bytes, &tmX, &cx.full[s], c_base, -p.p, c.z - p.p,
+                            p.src_first + c.y * p.NF, c.x);
+            };
+            for (int n = 0; n < my_tiles && n < p.stages; ++n) issue_load(n);
+            for (int n = 0; n < my_tiles; ++n) {
+                const int s = n % p.stages;
+                mbar_wait(&cx.done[s], (uint32_t)((n / p.stages) & 1));
+                const int3 c = tile_coord(n);
+                tma_store_5d(&tmY, ring + (size_t)s * p.in_bytes, c_base, 0, c.z, p.f_first + c.y * p.NF, c.x);
+                bulk_commit();
+                if (n + p.stages < my_tiles) {
+                    bulk_wait_read0();                      // the store has read the stage: it may be overwritten
+                    issue_load(n + p.stages);
+                }
+            }
+            bulk_wait0();
+        }
+        return;
+    }
+
+    // destination frames without a source frame are all zero: whole frames, round-robin over the grid
+    if (p.nzf > 0) {
+        const int frame16 = (int)((long long)p.Ho * p.Wo * p.C / 8);
+        const int nframes = p.B * p.nzf;
+        const int ncta = gridDim.x * gridDim.y;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int q = blockIdx.y * gridDim.x + blockIdx.x; q < nframes; q += ncta) {
+            const int f = p.zf[q % p.nzf], b = q / p.nzf;
+            uint4* dst = reinterpret_cast<uint4*>(y) + ((long long)b * p.To + f) * frame16;
+            for (int e = tid; e < frame16; e += DWM_COMPUTE) dst[e] = z;
+        }
+    }
+
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int win = g % p.NW, rowpair = g / p.NW;
+    // weight-table slots of this lane: b0 = P[e], b1 = P[e+8] with e = 2t - g (slot 7 holds zeros)
+    const int e0 = 2 * t - g;
+    const uint32_t slot0 = (uint32_t)((e0 >= -1 && e0 <= K - 1) ? e0 + 1 : 7) * 16;
+    const uint32_t slot1 = (uint32_t)((e0 + 8 >= -1 && e0 + 8 <= K - 1) ? e0 + 9 : 7) * 16;
+    const int col0 = win * p.VW + 2 * t;                  // first input column (tile coordinates) this lane reads
+    const int nfht = p.NF * p.Ht;
+    const uint32_t row_bytes = (uint32_t)p.Wi * pb;
+
+    for (int n = 0; n < my_tiles; ++n) {
+        const int s = n % p.stages;
+        mbar_wait(&cx.full[s], (uint32_t)((n / p.stages) & 1));
+        uint8_t* stage = ring + (size_t)s * p.in_bytes;
+
+        // A warp owns whole channel groups (4 channels = 8 bytes of every staged pixel) and walks their passes top
+        // to bottom.  Outputs replace the inputs in place: output (r, c) goes where input (r, c) was.  Nobody else
+        // touches this channel group's bytes, a pass has read everything it needs before it writes, and the rows it
+        // overwrites (its own destination rows) are not read by the passes below it.
+        for (int cg = warp; cg < p.NCG; cg += DWM_CWARPS) {
+            const uint8_t* wrow = tab + (uint32_t)(cg * K) * 128;
+            for (int pass = 0; pass < p.NP; ++pass) {
+                const int vr0 = pass * p.RP + 2 * rowpair;            // destination row (frame-major) of context g
+                const bool valid = vr0 < nfht;
+                const int vrc = valid ? vr0 : 0;
+                const int f = vrc / p.Ht;
+                const int in_row0 = vrc + f * (K - 1);                // frame f starts at row f*Hi of the staged tile
+                uint8_t* arow = stage + (uint32_t)in_row0 * row_bytes + (uint32_t)col0 * pb + (uint32_t)cg * 8;
+
+                float acc[NT][4][4];
+#pragma unroll
+                for (int a = 0; a < NT; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc[a][c][r] = 0.f;
+
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    // context g reads tile row r+i, context g+8 (the next destination row) tile row r+1+i
+                    RowFrag<NCH> r0, r1;
+                    load_row<NCH>(r0, arow + (uint32_t)i * row_bytes, pb);
+                    load_row<NCH>(r1, arow + (uint32_t)(i + 1) * row_bytes, pb);
+                    const uint4 b0 = lds128m(wrow + (uint32_t)i * 128 + slot0);
+                    const uint4 b1 = lds128m(wrow + (uint32_t)i * 128 + slot1);
+                    const uint32_t b0c[4] = {b0.x, b0.y, b0.z, b0.w};
+                    const uint32_t b1c[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                        for (int q = 0; q < NCH; ++q) {
+                            const uint32_t a0 = r0.lo[q][c], a1 = r1.lo[q][c], a2 = r0.hi[q][c], a3 = r1.hi[q][c];
+                            mma_bf16(acc[2 * q][c], a0, a1, a2, a3, b0c[c], b1c[c]);          // outputs 16q + 0..7
+                            mma_bf16(acc[2 * q + 1][c], a0, a1, a2, a3, 0u, b0c[c]);          // outputs 16q + 8..15 (k >= 8)
+                            if (q > 0) mma_bf16(acc[2 * q - 1][c], a0, a1, a2, a3, b1c[c], 0u); // ... and their k >= 16 part
+                        }
+                    }
+                }
+                __syncwarp();        // every lane has consumed its inputs (the MMAs are warp-wide): writes may start
+
+                // epilogue: (context h, column 8a + 2t + e) x 4 channels -> 8-byte pieces, in place
+                if (valid) {
+                    uint8_t* orow = stage + (uint32_t)in_row0 * row_bytes + (uint32_t)cg * 8;
+#pragma unroll
+                    for (int a = 0; a < NT; ++a) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int wl = 8 * a + 2 * t + e;              // column inside the window
+                            const int col = win * p.VW + wl;
+                            if (wl < p.VW && col < p.Wo) {
+                                uint8_t* o0 = orow + (uint32_t)col * pb;
+                                sts64m(o0, pack_bf16x2(acc[a][0][e], acc[a][1][e]), pack_bf16x2(acc[a][2][e], acc[a][3][e]));
+                                sts64m(o0 + row_bytes, pack_bf16x2(acc[a][0][2 + e], acc[a][1][2 + e]),
+                                       pack_bf16x2(acc[a][2][2 + e], acc[a][3][2 + e]));
+                            }
+                        }
+                    }
+                }
+                __syncwarp();        // ... and are complete before the next pass reads rows below
+            }
+        }
+        fence_proxy_async();                                   // in-place outputs -> visible to the TMA unit
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cx.done[s]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side planning
+// ------------------------------------------------------------------------------------------------
+static int make_map5_mma(CUtensorMap* tm, const void* base, int C, int W, int H, int T, int B, int bc, int bw, int bh, int bt) {
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)B};
+    uint64_t str[5] = {2, (uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)T * H * W * C * 2};
+    uint32_t box[5] = {(uint32_t)bc, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, 1};
+    return make_tmap_bf16(tm, base, 5, dims, str, box, 0);
+}
+
+static bool plan_mma(MmaPlan& p, int B, int C, int To, int Ho, int Wo, int K, int NCH, int f_count) {
+    p.B = B; p.C = C; p.To = To; p.Ho = Ho; p.Wo = Wo; p.p = K / 2;
+    p.VW = 16 * NCH - (K - 1);
+    const int nw = ceil_div(Wo, p.VW);
+    if (nw > 8) return false;                         // one tile spans the full width (in-place output, see the kernel)
+    p.NW = nw <= 1 ? 1 : nw <= 2 ? 2 : nw <= 4 ? 4 : 8;
+    p.RP = 2 * (8 / p.NW);
+    p.Wi = (p.NW - 1) * p.VW + 16 * NCH;
+    if (p.Wi > 256) return false;
+    // The TMA unit pays per box row (= one staged pixel of Cb*2 bytes; tools/tma_bench.cu): under 128 bytes per row
+    // it cannot keep up with HBM, so narrow layers stay on the CUDA-core kernels of dwconv_tiled.cu.
+    if (C < 64) return false;
+    double best = -1.0;
+    int bCb = 0, bHt = 0, bNF = 0, bSt = 0;
+    const int ho_even = (Ho + 1) / 2 * 2;
+    for (int nblk = ceil_div(C, 128); nblk <= ceil_div(C, 64); ++nblk) {
+        const int Cb = (ceil_div(C, nblk) + 7) / 8 * 8;
+        if (Cb < 64) break;
+        if ((nblk - 1) * Cb >= C) continue;                             // an empty last block
+        const int ncg = Cb / 4;
+        const int tab = ncg * K * 128;
+        for (int NF = 1; NF <= 4; ++NF) {
+            if (NF > 1 && NF > f_count) break;
+            for (int Ht = 2; Ht <= std::min(ho_even, 64); Ht += 2) {
+                if (NF > 1 && Ht < ho_even) continue;                    // several frames per tile only for whole planes
+                const int Hi = Ht + K - 1;
+                if (Hi > 256) break;
+                const long long inb = ((long long)NF * Hi * p.Wi * Cb * 2 + 127) / 128 * 128;
+                const long long left = DWM_SMEM_BUDGET - tab;
+                if (left < 2 * inb) continue;
+                const int st = (int)std::min<long long>(DWM_MAX_STAGES, left / inb);
+                const int NP = ceil_div(NF * Ht, p.RP);
+                const int th = ceil_div(Ho, Ht);
+                const double f_eff = (double)f_count / (ceil_div(f_count, NF) * NF);
+                const double useful = (double)Ho / th * NF * f_eff * Wo * ((double)C / nblk);
+                const double issued = (double)ceil_div(ncg, DWM_CWARPS) * DWM_CWARPS * 4.0 * NP * p.RP * p.NW * p.VW;
+                const double compute_eff = std::min(1.0, 1.6 * useful / issued);  // the math has headroom over the memory
+                const double halo = ((double)Ho / th * Wo) / ((double)Hi * p.Wi);   // useful share of the staged pixels
+                const double row_eff = std::min(1.0, Cb * 2 / 256.0);
+                const double score = compute_eff * (0.35 + 0.65 * halo) * (0.5 + 0.5 * row_eff) * (st >= 3 ? 1.0 : 0.9);
+                if (score > best + 1e-9) { best = score; bCb = Cb; bHt = Ht; bNF = NF; bSt = st; }
+            }
+        }
+    }
+    if (best < 0) return false;
+    p.Cb = bCb; p.NCG = bCb / 4; p.nblk = ceil_div(C, bCb);
+    p.Ht = bHt; p.NF = bNF; p.Hi = bHt + K - 1; p.stages = bSt;
+    p.NP = ceil_div(p.NF * p.Ht, p.RP);
+    p.tiles_h = ceil_div(Ho, p.Ht);
+    p.in_bytes = (int)(((long long)p.NF * p.Hi * p.Wi * p.Cb * 2 + 127) / 128 * 128);
+    p.tab_bytes = p.NCG * K * 128;
+    return true;
+}
+
+static bool dw_mma_enabled() {
+    static const bool on = [] { const char* e = getenv("PB_DW_MMA"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+// dst[b][to][ho][wo][c] = sum_{i,j} src[b][to - pT][ho + i - p][wo + j - p][c] * w[(flip) i*K + j][c]
+// with src of size (Ts, Hs, Ws) == spatially (Ho, Wo); destination frames without a source frame are zeroed.
+template <int K, int NCH>
+static bool launch_mma(const __nv_bfloat16* src, const float* w_tc, __nv_bfloat16* dst, int B, int C, int Ts, int To, int Ho,
+                       int Wo, int pT, int flip, cudaStream_t st) {
+    MmaPlan p{};
+    // destination frame `to` reads source frame to - pT
+    p.nzf = 0;
+    int first = -1, count = 0;
+    for (int f = 0; f < To; ++f) {
+        const int v = f - pT;
+        if (v >= 0 && v < Ts) { if (first < 0) first = f; ++count; }
+        else { if (p.nzf >= DWM_MAX_ZF || f > 255) return false; p.zf[p.nzf++] = (unsigned char)f; }
+    }
+    if (count == 0) return false;
+    if (!plan_mma(p, B, C, To, Ho, Wo, K, NCH, count)) return false;
+    p.f_first = first; p.f_count = count; p.src_first = first - pT;
+    p.tiles_f = ceil_div(count, p.NF);
+    p.ntiles = (long long)B * p.tiles_f * p.tiles_h;
+    if (p.ntiles >= (1LL << 31)) return false;
+    p.flip = flip;
+    CUtensorMap tmx, tmy;
+    if (make_map5_mma(&tmx, src, C, Wo, Ho, Ts, B, p.Cb, p.Wi, p.Hi, p.NF) != PB_OK) return false;
+    // The store reads the stage itself: full staged width (columns >= Wo are clipped by the TMA unit) and, with
+    // several frames per tile, the staged frame pitch Hi (rows >= Ho clipped: such tiles cover whole planes).
+    if (make_map5_mma(&tmy, dst, C, Wo, Ho, To, B, p.Cb, p.Wi, p.NF > 1 ? p.Hi : p.Ht, p.NF) != PB_OK) return false;
+    static unsigned long long once = 0;
+    if (ensure_dyn_smem(dw_s1_mma_kernel<K, NCH>, 226 * 1024, &once) != cudaSuccess) return false;
+    int ctas = std::max(1, 148 / p.nblk);
+    ctas = (int)std::min<long long>(ctas, p.ntiles);
+    if (p.stages > DWM_MAX_STAGES) p.stages = DWM_MAX_STAGES;
+    const size_t smem = (size_t)p.stages * p.in_bytes + p.tab_bytes + 128;
+    (void)launch_pdl(dw_s1_mma_kernel<K, NCH>, dim3(ctas, p.nblk), dim3(DWM_THREADS), smem, st, tmx, tmy, w_tc, dst, p);
+    return true;
+}
+
+static bool mma_class(const DwDims& d) {
+    return d.kT == 1 && d.kH == d.kW && (d.kH == 3 || d.kH == 5) && d.sH == 1 && d.sW == 1 && d.sT == 1 &&
+           d.pH == d.pW && d.pH == d.kH / 2 && d.C % 8 == 0 && d.Ho == d.H && d.Wo == d.W;
+}
+
+bool dw_fwd_mma(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y, const DwDims& d, cudaStream_t st) {
+    if (!dw_mma_enabled() || !mma_class(d)) return false;
+    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0) return false;
+    const bool one = d.W + d.kW - 1 <= 16;
+    if (d.kH == 3) return one ? launch_mma<3, 1>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st)
+                              : launch_mma<3, 2>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st);
+    return one ? launch_mma<5, 1>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st)
+               : launch_mma<5, 2>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st);
+}
+
+// stride-1 input gradient == correlation of dy with the flipped filter: dx[t] reads dy[t + pT]
+bool dw_dgrad_mma(const __nv_bfloat16* dy, const float* w_tc, __nv_bfloat16* dx, const DwDims& d, cudaStream_t st) {
+    if (!dw_mma_enabled() || !mma_class(d)) return false;
+    if (((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) != 0) return false;
+    const bool one = d.W + d.kW - 1 <= 16;
+    if (d.kH == 3) return one ? launch_mma<3, 1>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st)
+                              : launch_mma<3, 2>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st);
+    return one ? launch_mma<5, 1>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st)
+               : launch_mma<5, 2>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st);
+}
+
+}  // namespace pb

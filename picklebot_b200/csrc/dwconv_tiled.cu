@@ -635,8 +635,8 @@ static dim3 persistent_grid(const DwTile& p) {
 }
 
 template <typename KernelT>
-static void set_smem_once(KernelT k, std::once_flag& flag) {
-    std::call_once(flag, [k] { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); });
+static void set_smem_once(KernelT k, unsigned long long& done) {
+    (void)ensure_dyn_smem(k, 112 * 1024, &done);      // a failure surfaces as a launch error (caller's PB_CHECK_LAUNCH)
 }
 
 template <int K, int S, int WS>
@@ -650,7 +650,7 @@ static bool launch_fwd(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16*
     p.flip = flip;
     CUtensorMap tm;
     if (make_map5(&tm, x, d.C, d.W, d.H, d.T, d.B, p.Cb, p.Wi, p.Hi) != PB_OK) return false;
-    static std::once_flag once;
+    static unsigned long long once = 0;
     set_smem_once(dw_fwd_tma_kernel<K, S, WS>, once);
     (void)launch_pdl(dw_fwd_tma_kernel<K, S, WS>, dim3(persistent_grid(p)), dim3(DWT_THREADS),
                      (size_t)p.stages * p.stage_bytes + 128 + TAPS_BYTES, st,
@@ -669,7 +669,7 @@ static bool launch_dgrad_s2(const __nv_bfloat16* dy, const float* w_tc, __nv_bfl
     if (!plan_frames(p, d.T, d.To, 1, d.pT, d.sT)) return false;   // source frame = (t + pT)/sT
     CUtensorMap tm;
     if (make_map5(&tm, dy, d.C, d.Wo, d.Ho, d.To, d.B, p.Cb, p.Wi, p.Hi) != PB_OK) return false;
-    static std::once_flag once;
+    static unsigned long long once = 0;
     set_smem_once(dw_dgrad_s2_tma_kernel<K, XS>, once);
     (void)launch_pdl(dw_dgrad_s2_tma_kernel<K, XS>, dim3(persistent_grid(p)), dim3(DWT_THREADS),
                      (size_t)p.stages * p.stage_bytes + 128 + TAPS_BYTES, st,
@@ -690,7 +690,7 @@ static bool launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float*
     CUtensorMap tmx, tmd;
     if (make_map5(&tmx, x, d.C, d.W, d.H, d.T, d.B, p.Cb, p.Wi, p.Hi) != PB_OK) return false;
     if (make_map5(&tmd, dy, d.C, d.Wo, d.Ho, d.To, d.B, p.Cb, p.Wt, p.Ht) != PB_OK) return false;
-    static std::once_flag once;
+    static unsigned long long once = 0;
     set_smem_once(dw_wgrad_tma_kernel<K, S, WS>, once);
     (void)launch_pdl(dw_wgrad_tma_kernel<K, S, WS>, dim3(persistent_grid(p)), dim3(DWT_THREADS), (size_t)p.stages * p.stage_bytes + 128, st,
                        tmx, tmd, dw_tc, p);
@@ -710,6 +710,7 @@ static bool strip7(int wo) { return wo % 7 == 0; }
 template <> bool dw_fwd_tiled<__nv_bfloat16>(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y,
                                             const DwDims& d, cudaStream_t st) {
     if (!mobilenet_class(d) || !aligned16(x, y)) return false;
+    if (dw_fwd_mma(x, w_tc, y, d, st)) return true;            // stride 1: tensor-core kernel (dwconv_mma.cu)
     if (d.kH == 3 && d.sH == 1)
         return strip7(d.Wo) ? launch_fwd<3, 1, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st) : launch_fwd<3, 1, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
     if (d.kH == 3 && d.sH == 2)
@@ -730,6 +731,7 @@ template <> bool dw_dgrad_tiled<__nv_bfloat16>(const __nv_bfloat16* dy, const fl
         return d.kH == 3 ? launch_dgrad_s2<3>(dy, w_tc, dx, d, st) : launch_dgrad_s2<5>(dy, w_tc, dx, d, st);
     }
     if (d.sT != 1) return false;
+    if (dw_dgrad_mma(dy, w_tc, dx, d, st)) return true;        // tensor-core kernel (dwconv_mma.cu)
     DwDims r = d;                      // roles swapped: "input" = dy (To,Ho,Wo), "output" = dx (T,H,W)
     r.T = d.To; r.H = d.Ho; r.W = d.Wo;
     r.To = d.T; r.Ho = d.H; r.Wo = d.W;

@@ -19,9 +19,16 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double M, co
                                    long long* __restrict__ nbt, int C) {
     pdl_trigger();
     pdl_wait();
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && nbt && training) *nbt += 1;           // nn.BatchNorm's num_batches_tracked
-    if (c >= C) return;
+    // momentum < 0: nn.BatchNorm(momentum=None), the cumulative moving average with factor 1/num_batches_tracked
+    // (after the increment).  That mode is launched as ONE block so that every thread reads the old counter
+    // before thread 0 advances it.
+    if (momentum < 0.f) {
+        const long long seen = nbt ? *nbt : 0;
+        momentum = 1.f / (float)(seen + 1);
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nbt && training) *nbt += 1;           // nn.BatchNorm's num_batches_tracked
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
     float mean, var;
     if (training) {
         double s0 = 0, s1 = 0;
@@ -48,6 +55,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double M, co
     shift[c] = bta - mean * sc;
     if (mean_o) mean_o[c] = mean;
     if (invstd_o) invstd_o[c] = invstd;
+    }
 }
 
 template <int ACT> __device__ __forceinline__ float actf(float u, float slope) { return act_fwd(u, ACT, slope); }
@@ -312,7 +320,10 @@ extern "C" int pb_bn_finalize(const double* sums, long long M, const float* gamm
                               long long* num_batches_tracked, int C, pb_stream_t stream) {
     PB_REQUIRE(scale && shift && C > 0, "bn_finalize: bad args");
     PB_REQUIRE(training ? (sums != nullptr && M > 0) : (running_mean && running_var), "bn_finalize: missing statistics");
-    (void)launch_pdl(bn_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, (double)M,
+    const bool cumulative = momentum < 0.f;
+    PB_REQUIRE(!cumulative || !training || num_batches_tracked, "bn_finalize: momentum=None needs num_batches_tracked");
+    (void)launch_pdl(bn_finalize_kernel, dim3(cumulative ? 1 : ceil_div(C, 128)), dim3(cumulative ? 1024 : 128), 0,
+                     (cudaStream_t)stream, sums, (double)M,
                      gamma, beta, running_mean, running_var, training, momentum, eps, scale, shift, mean, invstd,
                      num_batches_tracked, C);
     PB_CHECK_LAUNCH("bn_finalize");

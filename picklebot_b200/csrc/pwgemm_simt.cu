@@ -216,6 +216,7 @@ extern "C" int pb_pw_gemm_simt(const void* A, const float* W, long long w_sn, lo
                          w_sk, bias, ascale, colscale, coladd, (T*)C, R, K, N);
     });
     PB_CHECK_LAUNCH("gemm_simt_kernel");
+    count_path(PB_PATH_GEMM_SIMT);
     return PB_OK;
 }
 
@@ -237,6 +238,7 @@ extern "C" int pb_pw_wgrad_simt(const void* A, const void* dC, const float* asca
                          dbias, M, R, K, N, rows);
     });
     PB_CHECK_LAUNCH("wgrad_simt_kernel");
+    count_path(PB_PATH_WGRAD_SIMT);
     return PB_OK;
 }
 

@@ -436,15 +436,10 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
         uint32_t box[3] = {(uint32_t)BK, (uint32_t)p.block_n, 1};
         if (int e = make_tmap_bf16(&tmW, W_bf16, 3, dims, str, box, BK * 2)) return e;
     }
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    });
+    static unsigned long long attr_done[3] = {0, 0, 0};
+    cudaError_t attr_err = ensure_dyn_smem(gemm_tc_kernel<false, false>, 226 * 1024, &attr_done[0]);
+    if (attr_err == cudaSuccess) attr_err = ensure_dyn_smem(gemm_tc_kernel<true, false>, 226 * 1024, &attr_done[1]);
+    if (attr_err == cudaSuccess) attr_err = ensure_dyn_smem(gemm_tc_kernel<false, true>, 226 * 1024, &attr_done[2]);
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(gemm_tc_kernel)");
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -460,5 +455,6 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
         PB_CUDA(launch_pdl(gemm_tc_kernel<false, false>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW,
                            p));
     PB_CHECK_LAUNCH("gemm_tc_kernel");
+    count_path(PB_PATH_GEMM_TC);
     return PB_OK;
 }

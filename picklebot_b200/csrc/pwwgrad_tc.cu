@@ -401,12 +401,9 @@ extern "C" int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, 
         uint32_t box[3] = {(uint32_t)pl.ew_a, (uint32_t)pl.rows, 1};
         if (int e = make_tmap_bf16(&tmA, A, 3, dims, str, box, pl.ew_a * 2)) return e;
     }
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    });
-    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_tc_kernel)");
+    static unsigned long long attr_done = 0;
+    if (cudaError_t attr_err = ensure_dyn_smem(wgrad_tc_kernel, 226 * 1024, &attr_done))
+        return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_tc_kernel)");
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -425,5 +422,6 @@ extern "C" int pb_pw_wgrad_tc(const void* A, const void* dC, const float* gate, 
                            pl.chunks * pl.fold, N, K));
         PB_CHECK_LAUNCH("wgrad_dgate_kernel");
     }
+    count_path(PB_PATH_WGRAD_TC);
     return PB_OK;
 }

@@ -190,15 +190,13 @@ using namespace pb;
 // shared-memory staging of FC_BT input vectors (+ the k-slice reduction scratch): allow up to 96 KB
 constexpr int FC_MAX_K = 2560;
 static int fc_smem_attrs() {
-    static cudaError_t err = [] {
-        const int bytes = 96 * 1024;
-        cudaError_t e = cudaFuncSetAttribute(fc_rows_kernel<PB_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fc_rows_kernel<PB_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fc_rows_kernel<PB_ACT_HSIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fc_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        return e;
-    }();
-    return err == cudaSuccess ? PB_OK : cuda_fail(err, "cudaFuncSetAttribute(fc kernels)");
+    static unsigned long long done[4] = {0, 0, 0, 0};
+    const int bytes = 96 * 1024;
+    cudaError_t e = ensure_dyn_smem(fc_rows_kernel<PB_ACT_NONE>, bytes, &done[0]);
+    if (e == cudaSuccess) e = ensure_dyn_smem(fc_rows_kernel<PB_ACT_RELU>, bytes, &done[1]);
+    if (e == cudaSuccess) e = ensure_dyn_smem(fc_rows_kernel<PB_ACT_HSIGMOID>, bytes, &done[2]);
+    if (e == cudaSuccess) e = ensure_dyn_smem(fc_cols_kernel, bytes, &done[3]);
+    return e == cudaSuccess ? PB_OK : cuda_fail(e, "cudaFuncSetAttribute(fc kernels)");
 }
 
 // Classifier-head linear layers (mobilenet.py:184-190, movinet.py:146-154): B = clips per call (64), so the

@@ -230,6 +230,7 @@ extern "C" int pb_stem_conv_fwd(const void* x, int x_dtype, STEM_ARGS, const flo
     PB_REQUIRE(x && w && y, "stem_conv_fwd: null pointer");
     if (stem_tc_eligible(d, y_dtype) && stem_tc_fwd(x, x_dtype, w, bias, y, kT, stem_tc_dims(d), (cudaStream_t)stream)) {
         PB_CHECK_LAUNCH("stem_tc_fwd_kernel");
+        count_path(PB_PATH_STEM_TC);
         return PB_OK;
     }
     long long P = (long long)B * To * Ho * Wo;
@@ -238,6 +239,7 @@ extern "C" int pb_stem_conv_fwd(const void* x, int x_dtype, STEM_ARGS, const flo
         stem_fwd_kernel<TX, TY><<<ceil_div(P, 128), 128, smem, (cudaStream_t)stream>>>((const TX*)x, w, bias, (TY*)y, d, P);
     });
     PB_CHECK_LAUNCH("stem_fwd_kernel");
+    count_path(PB_PATH_STEM_SIMT);
     return PB_OK;
 }
 
@@ -252,6 +254,7 @@ extern "C" int pb_stem_conv_wgrad(const void* x, int x_dtype, STEM_ARGS, const v
     if (dbias) PB_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, st));
     if (stem_tc_eligible(d, y_dtype) && stem_tc_wgrad(x, x_dtype, dy, dw, dbias, kT, stem_tc_dims(d), st)) {
         PB_CHECK_LAUNCH("stem_tc_wgrad_kernel");
+        count_path(PB_PATH_STEM_TC);
         return PB_OK;
     }
     long long P = (long long)B * To * Ho * Wo;
@@ -261,5 +264,6 @@ extern "C" int pb_stem_conv_wgrad(const void* x, int x_dtype, STEM_ARGS, const v
         stem_wgrad_kernel<TX, TY><<<ceil_div(P, per), 256, 0, st>>>((const TX*)x, (const TY*)dy, dw, dbias, d, P, per);
     });
     PB_CHECK_LAUNCH("stem_wgrad_kernel");
+    count_path(PB_PATH_STEM_SIMT);
     return PB_OK;
 }

@@ -139,7 +139,22 @@ class GradientBuckets:
         bucket = self.buckets[i]
         n = sum(p.numel() for p in bucket)
         flat = self._flat[i]
-        if not self.grad_as_bucket_view:
+        if self.grad_as_bucket_view:
+            # the views must still be what autograd accumulated into: optimizer.zero_grad(set_to_none=True) or a
+            # ``p.grad = ...`` assignment silently detaches them, and the all-reduce below would then average stale
+            # buffers.  Re-attach (copy the fresh gradient into the view) instead of losing the synchronisation.
+            off = 0
+            for p in bucket:
+                view = flat[off:off + p.numel()]
+                g = p.grad
+                if g is None:
+                    view.zero_()
+                    p.grad = view.view_as(p)
+                elif g.data_ptr() != view.data_ptr():
+                    view.copy_(g.reshape(-1))
+                    p.grad = view.view_as(p)
+                off += p.numel()
+        else:
             if flat is None or flat.device != bucket[0].device:
                 flat = torch.empty(n, dtype=torch.float32, device=bucket[0].device)
                 self._flat[i] = flat

@@ -33,7 +33,8 @@ def _act_code(m: nn.Module):
 
 
 def _bn_args(bn: nn.BatchNorm3d):
-    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    # momentum=None is nn.BatchNorm's cumulative moving average; pb_bn_finalize takes it as a negative momentum
+    mom = -1.0 if bn.momentum is None else float(bn.momentum)
     return float(bn.eps), mom, bn.running_mean, bn.running_var, bn.num_batches_tracked
 
 

@@ -213,10 +213,10 @@ class MoViNetA2(nn.Module):
                 mask1d = torch.empty((B, 2048), dtype=torch.float32, device=x.device).bernoulli_(1 - d1.p).div_(1 - d1.p)
         bn0, bn1 = self.conv[1], self.classifier[3]
         eps0, mom0, rm0, rv0, nbt0 = _bn_args(bn0)
-        _, _, rm1, rv1, nbt1 = _bn_args(bn1)
+        eps1, mom1, rm1, rv1, nbt1 = _bn_args(bn1)
         fc1, fc2 = self.classifier[2], self.classifier[6]
-        return MoViNetTailFn.apply(x, self._cache, bn0.training, eps0, mom0, mask3d, mask1d,
-                                   rm0, rv0, nbt0, rm1, rv1, nbt1,
+        return MoViNetTailFn.apply(x, self._cache, (bn0.training, bn1.training), (eps0, eps1), (mom0, mom1),
+                                   mask3d, mask1d, rm0, rv0, nbt0, rm1, rv1, nbt1,
                                    self.conv[0].weight, bn0.weight, bn0.bias,
                                    fc1.weight, fc1.bias, bn1.weight, bn1.bias, fc2.weight, fc2.bias)
 
@@ -254,7 +254,7 @@ class MoViNetA2(nn.Module):
         u1 = ops.gemm_simt(feat, fc1.weight, 2048, 640, 640, 1, bias=fc1.bias)
         _, _, rm1, rv1, _ = _bn_args(bn1)
         h1, _ = blocks.bn_forward(u1, B, 2048, bn1.weight, bn1.bias, rm1, rv1, None, False, float(bn1.eps), 0.1, hs,
-                                  0.0, None)
+                                  0.0, None)   # eval mode: the momentum argument is unused
         logits = ops.gemm_simt(h1, fc2.weight, self.num_classes, 2048, 2048, 1, bias=fc2.bias)
         return logits, state
 

@@ -91,4 +91,7 @@ class AdamW(torch.optim.Optimizer):
                  n, n_chunks, float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
                  float(group["weight_decay"]), float(1.0 - beta1 ** t), float(math.sqrt(1.0 - beta2 ** t)),
                  float(grad_scale), _st())
+            # The kernel wrote the parameters through raw pointers: tell torch (and blocks.WeightCache, which keys the
+            # bf16 / transposed / tap-major shadow copies on Parameter._version) that they changed.
+            torch.autograd.graph.increment_version(plist)
         return loss

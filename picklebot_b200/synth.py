@@ -85,6 +85,41 @@ def synthetic_clips_u8_device(batch: int, frames: int, height: int, width: int, 
     return torch.clamp(img + noise - 6, 0, 255).to(torch.uint8)
 
 
+def synthetic_task_clips_u8(batch: int, frames: int = 8, height: int = 64, width: int = 64,
+                            seed: int = SEED_DATA) -> Tuple[torch.Tensor, torch.Tensor]:
+    """A separable two-class toy task in the clip family above (the argmax check needs a
+    checkpoint whose decisions are not all the same class): class 1 = a warm (red-dominant) bump moving to the
+    right, class 0 = a cold (blue-dominant) bump moving to the left, over a random grey background with 5 %
+    noise.  Returns (uint8 (B,T,H,W,3), int64 labels (B,)).  Integer arithmetic only: bit-reproducible."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    B, T, H, W = batch, frames, height, width
+    labels = torch.randint(0, 2, (B,), generator=g)
+    lab = labels.view(B, 1, 1, 1)
+    grey = torch.randint(60, 160, (B, 1, 1, 1, 1), generator=g)
+    bg = grey + torch.randint(-12, 13, (B, 1, 1, 1, 3), generator=g)
+    strong = torch.randint(170, 256, (B, 1, 1, 1), generator=g)
+    weak = torch.randint(0, 90, (B, 1, 1, 1), generator=g)
+    mid = torch.randint(40, 140, (B, 1, 1, 1), generator=g)
+    red = torch.where(lab == 1, strong, weak)
+    blue = torch.where(lab == 1, weak, strong)
+    fg = torch.stack([red, mid, blue], dim=-1)                       # (B,1,1,1,3)
+    speed = torch.randint(2, max(3, W // 10), (B, 1, 1, 1), generator=g)
+    vx = torch.where(lab == 1, speed, -speed)
+    vy = torch.randint(-2, 3, (B, 1, 1, 1), generator=g)
+    cx0 = torch.randint(W // 4, 3 * W // 4, (B, 1, 1, 1), generator=g)
+    cy0 = torch.randint(H // 4, 3 * H // 4, (B, 1, 1, 1), generator=g)
+    rad = torch.randint(max(4, H // 8), max(6, H // 4), (B, 1, 1, 1), generator=g)
+    t = torch.arange(T).view(1, T, 1, 1) - T // 2
+    ys = torch.arange(H).view(1, 1, H, 1)
+    xs = torch.arange(W).view(1, 1, 1, W)
+    d2 = (xs - (cx0 + vx * t)) ** 2 + (ys - (cy0 + vy * t)) ** 2
+    r2 = rad * rad
+    bump = (torch.clamp(r2 - d2, min=0) * 256 // r2).unsqueeze(-1)
+    img = bg + (fg - bg) * bump // 256
+    noise = torch.randint(0, 13, (B, T, H, W, 3), generator=g)
+    return torch.clamp(img + noise - 6, 0, 255).to(torch.uint8), labels
+
+
 def clips_to_features(clips_u8: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """The reference's ``extract_features_labels`` (train.py:102-108): a ``(B,C,T,H,W)`` view with
     channels-last-3d strides, cast and divided by 255 (same op order, so bf16 values match)."""

@@ -47,8 +47,11 @@ def features(shape, seed=synth.SEED_DATA, dtype=torch.float32, device="cpu", cha
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """Norm-wise relative error ||a-b|| / ||b|| (many logits are ~1e-2)."""
-    a = a.detach().double().cpu()
-    b = b.detach().double().cpu()
+    if a.is_cuda and b.is_cuda:              # large activations: reduce on the device, in fp64
+        a, b = a.detach().double(), b.detach().double()
+    else:
+        a = a.detach().double().cpu()
+        b = b.detach().double().cpu()
     den = float(b.norm())
     return float((a - b).norm()) / (den if den > 0 else 1.0)
 

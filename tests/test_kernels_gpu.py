@@ -52,7 +52,18 @@ DW_CASES = [
     (2, 672, 16, 14, 14, (1, 3, 3), (1, 1, 1), (1, 1, 1)),    # block4.5
     (2, 672, 18, 14, 14, (1, 5, 5), (2, 2, 2), (2, 2, 2)),    # block5.0
     (2, 960, 11, 7, 7, (1, 5, 5), (1, 1, 1), (2, 2, 2)),      # block5.1
+    # window / tile edges of the tensor-core stride-1 kernels (dwconv_mma.cu)
+    (3, 64, 1, 13, 31, (1, 3, 3), (1, 1, 1), (1, 1, 1)),      # one frame in, odd sizes, 2 windows with a ragged second one
+    (1, 200, 5, 29, 12, (1, 5, 5), (1, 1, 1), (2, 2, 2)),     # 12 columns = exactly one 16-wide chunk, odd height
+    (2, 136, 3, 9, 61, (1, 3, 3), (1, 1, 1), (1, 1, 1)),      # 61 columns: 3 windows padded to 4, ragged channel block
+    (1, 64, 2, 5, 113, (1, 5, 5), (1, 1, 1), (2, 2, 2)),      # 113 columns: 5 windows padded to 8
+    (5, 72, 3, 7, 7, (1, 5, 5), (1, 1, 1), (2, 2, 2)),        # 7x7 planes, odd frame count (two frames per tile)
 ]
+
+# (case index) -> must be served by the TMA fast paths in all three directions (every MobileNet class shape)
+def _is_mobilenet_class(k, s, p):
+    return k[0] == 1 and k[1] == k[2] and k[1] in (3, 5) and s[0] == s[1] == s[2] and s[0] in (1, 2) \
+        and p[0] == p[1] == p[2] == k[1] // 2
 
 
 @pytest.mark.parametrize("dt", DTYPES)
@@ -60,9 +71,11 @@ DW_CASES = [
 def test_dwconv_fwd_dgrad_wgrad(case, dt):
     from picklebot_b200 import ops
     B, C, T, H, W, k, s, p = case
+    from picklebot_b200 import _lib
     x = rnd(B, T, H, W, C, dt=dt, seed=1)
     w = rnd(C, 1, *k, seed=2, scale=0.5)
     w_tc = ops.dw_weight_tapmajor(w, dt)
+    _lib.path_reset()
     y = ops.dwconv_fwd(x, w_tc, k, s, p)
     # torch reference in fp32 on the same (rounded) operands
     xr = x.float().permute(0, 4, 1, 2, 3).requires_grad_(True)
@@ -77,6 +90,12 @@ def test_dwconv_fwd_dgrad_wgrad(case, dt):
     dw_tc = ops.dwconv_wgrad(x, dy, k, s, p)
     dw = ops.dw_weight_grad_from_tapmajor(dw_tc, w.shape)
     assert rel_err(dw, wr.grad) < (1e-4 if dt == torch.float32 else 2e-3)
+    paths = _lib.path_counts()
+    if dt == torch.bfloat16 and _is_mobilenet_class(k, s, p) and (s[0] == 1 or min(H, W) >= 2):
+        # production path: no silent fall-through to the one-pixel-per-thread kernels
+        assert paths["dw_fwd_tma"] == 1 and paths["dw_dgrad_tma"] == 1 and paths["dw_wgrad_tma"] == 1, paths
+    else:
+        assert paths["dw_fwd_generic"] == 1 and paths["dw_dgrad_generic"] == 1 and paths["dw_wgrad_generic"] == 1, paths
 
 
 @pytest.mark.parametrize("dt", DTYPES)

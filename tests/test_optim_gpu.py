@@ -82,3 +82,66 @@ def test_cross_entropy_loss_gradient_and_accuracy(B, NC):
     assert torch.allclose(logits.grad, ref_logits.grad, rtol=1e-5, atol=1e-8)
     assert int(correct) == int((ref_logits.argmax(1) == labels).sum())
     assert correct.dtype == torch.int32 and not correct.requires_grad
+
+
+def test_model_with_adamw_eager_steps_follow_the_optimizer():
+    """The optimizer writes parameters through raw pointers; the modules' cached bf16 / transposed / tap-major weight
+    copies (blocks.WeightCache, keyed on Parameter._version) must be rebuilt after every step.  Two eager training
+    steps of a small MobileNetLarge3D under bf16 autocast with picklebot_b200.optim.AdamW against the same model
+    driven by torch.optim.AdamW (whose in-place updates bump the versions themselves)."""
+    import picklebot_b200 as pb
+    from picklebot_b200 import synth
+    from picklebot_b200.optim import AdamW
+    from _util import rel_err, synthetic_checkpoint
+    shape = (4, 8, 64, 64)
+    clips = synth.synthetic_clips_u8(*shape).cuda().permute(0, 4, 1, 2, 3)
+    labels = synth.synthetic_labels(shape[0], 2).cuda()
+    g = torch.Generator().manual_seed(7)
+    from oracle import picklebot_oracle as O
+    masks = [[torch.empty(shape[0], row[1]).bernoulli_(0.8, generator=g) / 0.8
+              for rows in O.LARGE_BLOCKS.values() for row in rows] for _ in range(3)]
+    models, opts = [], []
+    for kind in ("ours", "torch"):
+        m = pb.MobileNetLarge3D(num_classes=2)
+        m.load_state_dict(synthetic_checkpoint("MobileNetLarge3D"))
+        m = m.cuda().train()
+        models.append(m)
+        opts.append(AdamW(m.parameters(), lr=1e-2, weight_decay=1e-2) if kind == "ours"
+                    else torch.optim.AdamW(m.parameters(), lr=1e-2, weight_decay=1e-2))
+    w0 = models[0].block3[1].depthwise_conv.weight.detach().clone()
+    losses = [[], []]
+    for step in range(3):
+        for j, (m, opt) in enumerate(zip(models, opts)):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = torch.nn.functional.cross_entropy(m(clips, _masks=[t.clone() for t in masks[step]]).float(), labels)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            losses[j].append(float(loss))
+    # lr 1e-2 moves every weight by ~1e-2 per step: with stale shadow copies the second and third losses differ grossly
+    assert float((models[0].block3[1].depthwise_conv.weight - w0).abs().max()) > 5e-3
+    for a, b in zip(losses[0], losses[1]):
+        assert abs(a - b) < 2e-2 * max(1.0, abs(b)), (losses[0], losses[1])
+    pa, pb_ = dict(models[0].named_parameters()), dict(models[1].named_parameters())
+    flat_a = torch.cat([pa[k].detach().flatten() for k in pa])
+    flat_b = torch.cat([pb_[k].detach().flatten() for k in pa])
+    # two bf16 runs differ by the order of their atomics (measured 2.7e-2 after three lr = 1e-2 steps); stale weight
+    # shadows would leave the convolutions at their initial values: an O(1) difference
+    assert rel_err(flat_a, flat_b) < 8e-2, rel_err(flat_a, flat_b)
+
+
+def test_ce_loss_ignores_out_of_range_labels():
+    """ignore_index-style labels (-100) must not be used as an index: same loss/gradient as torch's CrossEntropyLoss."""
+    from picklebot_b200 import loss as pbloss
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(9, 5, generator=g).cuda().requires_grad_(True)
+    labels = torch.tensor([0, 4, -100, 2, 1, -100, 3, 3, 0]).cuda()
+    l, correct = pbloss.cross_entropy_with_accuracy(logits, labels)
+    l.backward()
+    ref_logits = logits.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_logits, labels)            # ignore_index = -100, mean over the rest
+    ref.backward()
+    assert abs(float(l) - float(ref)) < 1e-5
+    assert torch.allclose(logits.grad, ref_logits.grad, atol=1e-6)
+    valid = labels >= 0
+    assert int(correct) == int((logits.detach().argmax(1)[valid] == labels[valid]).sum())
