@@ -353,37 +353,46 @@ def main():
     assert args.global_batch % (micro * world) == 0
     accum = args.global_batch // (micro * world)
 
+    cfg = CONFIGS[args.config]
+    mode, clip_shape, nc = cfg["mode"], cfg["clip"], cfg["nc"]
+    train = mode == "train"
     torch.manual_seed(1234)
-    model = pb.MobileNetLarge3D(num_classes=NUM_CLASSES)
+    model = pb.valid_models[cfg["model"]](num_classes=nc)
     model.load_state_dict(synth.synthetic_state_dict(model.state_dict()))
-    model = model.to(dev).train()
+    model = model.to(dev)
+    model = model.train() if train else model.eval()
     net = model
     buckets = None
-    if world > 1:
+    if world > 1 and train:
         if args.dp == "ddp":
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
         else:
             from picklebot_b200 import dp as pbdp
             pbdp.broadcast_module(model)
             buckets = pbdp.GradientBuckets(model.parameters(), grad_as_bucket_view=True)
-    if args.torch_optim:
+    opt = None
+    if not train:
+        pass
+    elif args.torch_optim:
         opt = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=5e-4, fused=True)
     else:
         from picklebot_b200.optim import AdamW          # one pb_adamw_step launch over all ~170 tensors
         opt = AdamW(model.parameters(), lr=3e-4, weight_decay=5e-4)
-    use_graph = not args.no_graphs and args.dp == "buckets"
+    use_graph = not args.no_graphs and args.dp == "buckets" and mode != "stream"
     from picklebot_b200 import loss as pbloss               # cross-entropy + accuracy count in one kernel (pb_ce_loss)
 
     # synthetic uint8 clips: this rank's shard of each global batch, distinct per micro-batch
-    clips = [synth.synthetic_clips_u8_device(micro, *CLIP, seed=1000 * rank + a, device=dev) for a in range(accum)]
-    labels = [synth.synthetic_labels(micro, NUM_CLASSES, seed=77 + 1000 * rank + a).to(dev) for a in range(accum)]
-    loss_buf = torch.zeros((), device=dev)
+    clips = [synth.synthetic_clips_u8_device(micro, *clip_shape, seed=1000 * rank + a, device=dev) for a in range(accum)]
+    labels = [synth.synthetic_labels(micro, nc, seed=77 + 1000 * rank + a).to(dev) for a in range(accum)]
 
     # One micro-batch = forward + loss + backward.  Default: captured once in a CUDA graph and replayed (issuing the
     # ~370 launches from Python costs the host ~11 ms per 14 ms of GPU work, which starves the GPUs once eight
     # processes share the box's cores); gradients accumulate in place, the exchange runs after the last replay.
-    gstep = None
-    if use_graph:
+    gstep = gfwd = None
+    if use_graph and not train:
+        from picklebot_b200.graph import GraphedForward
+        gfwd = GraphedForward(model, clips[0].permute(0, 4, 1, 2, 3))
+    if use_graph and train:
         from contextlib import nullcontext
         from picklebot_b200.graph import GraphedTrainStep
         with (buckets.no_sync() if buckets is not None else nullcontext()):
@@ -399,7 +408,24 @@ def main():
         else:
             torch._foreach_zero_(grad_list)     # the graph accumulates into these very tensors
 
+    def stream_clip(x_u8):
+        """One batch of long clips through the causal streaming path, chunk by chunk; the stream state (tail frames
+        of every temporal conv, cumulative squeeze-excite / head sums) lives on the device between the calls."""
+        state = model.init_stream_state()
+        logits = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            for t0 in range(0, clip_shape[0], cfg["chunk"]):
+                logits, state = model.forward_stream(x_u8[:, t0:t0 + cfg["chunk"]].permute(0, 4, 1, 2, 3), state)
+        return logits
+
     def micro_step(x_u8, y, sync_grads, eager=False):
+        if mode == "stream":
+            return stream_clip(x_u8)
+        if mode == "infer":
+            if gfwd is not None and not eager:
+                return gfwd(x_u8.permute(0, 4, 1, 2, 3))
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                return model(x_u8.permute(0, 4, 1, 2, 3))
         if gstep is not None and not eager:
             loss = gstep(x_u8.permute(0, 4, 1, 2, 3), y)
             if sync_grads and buckets is not None:
@@ -422,9 +448,10 @@ def main():
         tot = None
         for a in range(accum):
             l = micro_step(clips[a], labels[a], a == accum - 1, eager)
-            tot = l if tot is None else tot + l
-        opt.step()
-        zero_grads()
+            tot = l if (tot is None or not train) else tot + l
+        if train:
+            opt.step()
+            zero_grads()
         return tot
 
     def barrier():
@@ -455,8 +482,8 @@ def main():
     n0 = _lib.launch_count()
     ms = timed(step_resident, args.steps)
     launches = _lib.launch_count() - n0
-    if gstep is not None:                       # replays launch the captured kernels without passing the C ABI
-        launches += args.steps * accum * gstep.launches
+    if gstep is not None or gfwd is not None:   # replays launch the captured kernels without passing the C ABI
+        launches += args.steps * accum * (gstep or gfwd).launches
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = args.global_batch / (ms_per_step / 1000.0)
@@ -471,7 +498,9 @@ def main():
         lbuf = [torch.empty_like(labels[0]) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
-        host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+        # what the user reads back every step: the loss (training) or the logits of the last micro-batch (inference)
+        host_loss = (torch.zeros((), dtype=torch.float32) if train else
+                     torch.zeros((micro, nc), dtype=torch.float32)).pin_memory()
 
         def upload(a, slot):
             with torch.cuda.stream(copy_stream):
@@ -491,13 +520,14 @@ def main():
                 cur.wait_event(ready[slot])
                 l = micro_step(dbuf[slot], lbuf[slot], a == accum - 1)
                 consumed[slot].record(cur)
-                tot = l if tot is None else tot + l
+                tot = l if (tot is None or not train) else tot + l
                 seq[0] += 1
-            opt.step()
-            zero_grads()
-            host_loss.copy_(tot, non_blocking=True)
-            torch.cuda.current_stream().synchronize()          # the user reads the loss every step
-            return float(host_loss)
+            if train:
+                opt.step()
+                zero_grads()
+            host_loss.copy_(tot.float(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()          # the user reads the result every step
+            return host_loss
 
         for s in range(2):
             consumed[s].record(torch.cuda.current_stream())
@@ -506,7 +536,7 @@ def main():
         ms_e = timed(step_e2e, args.steps) / args.steps
         e2e = {"value": args.global_batch / (ms_e / 1000.0), "unit": "clips/s",
                "h2d_bytes_per_step": accum * (clips[0].numel() + labels[0].numel() * 8),
-               "d2h_bytes_per_step": 4, "ms_per_step": ms_e}
+               "d2h_bytes_per_step": host_loss.numel() * 4, "ms_per_step": ms_e}
         del host_clips, dbuf
 
     # ---- per-kernel roofline: instrumented steps (CUDA events around every launch) -----------------
@@ -557,42 +587,52 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        best, mean, times = cpu_train_clips_per_s(4, reps=3, warm=1)
+        cb = cpu_batch(cfg)
+        best, mean, times = cpu_clips_per_s(cfg, cb, reps=3 if train else 2, warm=1)
         cpu = {"value": mean, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"{len(times)} train steps (fwd+CE+bwd) of 4 clips 3x16x224x224, fp32, oracle "
+               "sample": f"{len(times)} {CPU_SAMPLE[mode]} of {cb} clips 3x{'x'.join(map(str, clip_shape))}, fp32, oracle "
                          f"(torch-op restatement of the reference) on the host cores"}
 
     torch_b200 = None
-    if rank == 0 and world == 1 and not args.no_torch_b200:
+    if rank == 0 and world == 1 and not args.no_torch_b200 and mode != "stream":    # (no reference streaming path exists)
         torch.cuda.empty_cache()
         torch_b200 = torch_b200_legs(args, local)
-        for mode in ("eager", "compiled"):
-            if "value" in torch_b200.get(mode, {}):
-                torch_b200[mode]["ours_over_torch"] = value / torch_b200[mode]["value"]
+        for leg in ("eager", "compiled"):
+            if "value" in torch_b200.get(leg, {}):
+                torch_b200[leg]["ours_over_torch"] = value / torch_b200[leg]["value"]
 
     if rank == 0:
+        clip_mb = clips[0].numel() / 1e6
+        conf = {"workload": cfg["workload"], "baseline_config": args.config,
+                "global_batch": args.global_batch, "micro_batch_per_gpu": micro, "accum_steps": accum,
+                "parallelism": f"dp{world}", "clip": list(clip_shape),
+                "l2": f"inputs larger than L2 ({clip_mb:.0f} MB uint8 per micro-batch, distinct buffers); no flush",
+                "num_classes": nc}
+        if train:
+            conf.update({
+                "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                      "picklebot_b200.dp.GradientBuckets: .grad tensors are views of the bucket "
+                                      "buffers, in-place NCCL all-reduce once per optimizer step" + (
+                                          " after the last graph replay" if gstep is not None else
+                                          ", launched from post-accumulate-grad hooks") if args.dp == "buckets"
+                                      else "torch DDP, no_sync on all but the last micro-batch"),
+                "launch": ("forward+loss+backward of a micro-batch captured once in a CUDA graph "
+                           "(picklebot_b200.graph.GraphedTrainStep) and replayed; clips are copied device-to-"
+                           "device into the graph's static input" if gstep is not None else "eager"),
+                "criterion": "picklebot_b200.loss.cross_entropy (pb_ce_loss), mean over the micro-batch / accum_steps",
+                "optimizer": ("torch.optim.AdamW(fused=True)" if args.torch_optim else
+                              "picklebot_b200.optim.AdamW (multi-tensor pb_adamw_step)") + " inside the timed region"})
+        elif mode == "infer":
+            conf["launch"] = ("eval forward of a micro-batch captured once in a CUDA graph (picklebot_b200.graph."
+                              "GraphedForward) and replayed" if gfwd is not None else "eager")
+        else:
+            conf["launch"] = (f"eager: {clip_shape[0] // cfg['chunk']} forward_stream calls per clip batch, stream state "
+                              f"resident on the device between calls")
         line = {
-            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "MobileNetLarge3D training step, bf16 autocast, synthetic uint8 clips 3x16x224x224 "
-                                   "(BASELINE.json configs[2])",
-                       "global_batch": args.global_batch, "micro_batch_per_gpu": micro, "accum_steps": accum,
-                       "parallelism": f"dp{world}",
-                       "gradient_exchange": ("none (1 GPU)" if world == 1 else
-                                             "picklebot_b200.dp.GradientBuckets: .grad tensors are views of the bucket "
-                                             "buffers, in-place NCCL all-reduce once per optimizer step" + (
-                                                 " after the last graph replay" if gstep is not None else
-                                                 ", launched from post-accumulate-grad hooks") if args.dp == "buckets"
-                                             else "torch DDP, no_sync on all but the last micro-batch"),
-                       "launch": ("forward+loss+backward of a micro-batch captured once in a CUDA graph "
-                                  "(picklebot_b200.graph.GraphedTrainStep) and replayed; clips are copied device-to-"
-                                  "device into the graph's static input" if gstep is not None else "eager"),
-                       "criterion": "picklebot_b200.loss.cross_entropy (pb_ce_loss), mean over the micro-batch / accum_steps",
-                       "optimizer": ("torch.optim.AdamW(fused=True)" if args.torch_optim else
-                                     "picklebot_b200.optim.AdamW (multi-tensor pb_adamw_step)") + " inside the timed region",
-                       "l2": "inputs larger than L2 (154 MB uint8 per micro-batch, distinct buffers); no flush",
-                       "num_classes": NUM_CLASSES},
+            "metric": cfg["metric"], "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": conf,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "torch_b200": torch_b200, "kernels": kernels,
         }

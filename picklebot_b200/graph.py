@@ -96,3 +96,43 @@ class GraphedTrainStep:
             self.y.copy_(y, non_blocking=True)
         self.graph.replay()
         return self.loss
+
+
+class GraphedForward:
+    """Inference twin of ``GraphedTrainStep``: ``fwd = GraphedForward(model.eval(), example_x)``; ``logits = fwd(x)``
+    copies ``x`` into the graph's static input (device-to-device or from pinned host memory) and replays the captured
+    eval-mode forward under bf16 autocast.  The returned logits tensor is static (read it before the next replay)."""
+
+    def __init__(self, model: torch.nn.Module, example_x: torch.Tensor,
+                 autocast_dtype: Optional[torch.dtype] = torch.bfloat16, warmup: int = 2):
+        if not example_x.is_cuda:
+            raise ValueError("GraphedForward: inputs must live on the GPU")
+        if model.training:
+            raise ValueError("GraphedForward captures an inference pass: call model.eval() first")
+        self.model, self.autocast_dtype = model, autocast_dtype
+        self.x = torch.empty_strided(example_x.shape, example_x.stride(), dtype=example_x.dtype, device=example_x.device)
+        self.x.copy_(example_x)
+        side = torch.cuda.Stream(device=example_x.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        before = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.logits = self._eager()
+        self.launches = _lib.launch_count() - before
+
+    @torch.no_grad()
+    def _eager(self) -> torch.Tensor:
+        if self.autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                return self.model(self.x)
+        return self.model(self.x)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        if x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.logits

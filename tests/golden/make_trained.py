@@ -38,7 +38,7 @@ EVAL_CLIPS, EVAL_SEED = 96, 900001
 CASES = {
     "MobileNetLarge3D": (ref_mobilenet.MobileNetLarge3D, 300, 0.002),
     "MobileNetSmall3D": (ref_mobilenet.MobileNetSmall3D, 300, 0.02),
-    "MoViNetA2": (ref_movinet.MoViNetA2, 240, 0.002),
+    "MoViNetA2": (ref_movinet.MoViNetA2, 450, 0.004),
 }
 
 

@@ -108,3 +108,37 @@ def test_shard_range():
         dp.shard_range(0, 3, 512, 64)
     with pytest.raises(ValueError):
         dp.shard_range(0, 2, 512, 96)
+
+
+def _eval_worker(rank, world, port, out):
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from picklebot_b200.evalloop import estimate_loss
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        torch.manual_seed(0)
+        model = nn.Sequential(nn.Flatten(), nn.Linear(3 * 2 * 4 * 4, 5))            # stands in for the CUDA models
+        g = torch.Generator().manual_seed(1)
+        data = [(torch.randint(0, 256, (6, 2, 4, 4, 3), generator=g, dtype=torch.uint8),
+                 torch.randint(0, 5, (6, 1), generator=g)) for _ in range(4)]
+        shard = data[rank::world]                                                    # DistributedSampler-like split
+        kw = dict(use_autocast=False, feature_dtype=torch.float32)
+        local = estimate_loss(model, shard, F.cross_entropy, "cpu", all_reduce=False, **kw)
+        glob = estimate_loss(model, shard, F.cross_entropy, "cpu", all_reduce=True, **kw)
+        full = estimate_loss(model, data, F.cross_entropy, "cpu", all_reduce=False, **kw)
+        torch.save((local, glob, full), f"{out}.{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_estimate_loss_all_reduced_over_ranks(tmp_path):
+    """evalloop.estimate_loss: per-rank numbers are the reference's (train.py:123-153 on that rank's shard); the
+    all-reduced numbers equal a single-process pass over the whole validation set."""
+    out = str(tmp_path / "eval")
+    mp.spawn(_eval_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    (l0, g0, f0), (l1, g1, f1) = torch.load(out + ".0"), torch.load(out + ".1")
+    assert g0 == pytest.approx(g1) and g0 == pytest.approx(f0, rel=1e-6)
+    assert l0 != pytest.approx(l1)                       # the shards differ, so do the reference-style numbers
+    assert g0[0] == pytest.approx((l0[0] + l1[0]) / 2, rel=1e-6)
