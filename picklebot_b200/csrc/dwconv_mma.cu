@@ -15,12 +15,19 @@
 //     B_i[k][n] = w[i][k - n]  (0 <= k-n < K, else 0)      the filter row as a banded (Toeplitz) matrix
 //     D[m][n]   = output pixel wbase(m) + n of context m
 //
-// A window is NCH chunks of 16 input columns and yields 16*NCH - (K-1) outputs; output columns 8..15 of a chunk
-// reuse the same B registers shifted by 8 ({0,b0} / {b1,0}), so a lane holds 2 weight registers per (channel, i).
-// A lane owns contexts g and g+8 (g = lane/4), two consecutive destination rows.  Fragments are built from 8-byte
-// shared-memory loads (4 channels of one pixel) with one PRMT per register (pixel pair of one channel): ~0.5 ALU
-// instructions per staged element and filter row instead of ~1 per tap.  Products are exact and accumulate in
-// fp32, like the CUDA-core kernels.  Instruction budget: ~5 (3x3) / ~9 (5x5) per output element.
+// A window is 16 input columns and yields 16 - (K-1) outputs; output columns 8..15 reuse the same B registers
+// shifted by 8 ({0,b0}), so a lane holds 2 weight registers per (channel, i).  A lane owns contexts g and g+8
+// (g = lane/4).  Fragments are built from 16-byte shared-memory loads (8 channels of one pixel) with one PRMT per
+// register (pixel pair of one channel): ~0.5 ALU instructions per staged element and filter row instead of ~1 per
+// tap.  Products are exact and accumulate in fp32, like the CUDA-core kernels.  Instruction budget: ~4 (3x3) /
+// ~7 (5x5) per output element.
+//
+// Shared-memory banks decide the layout (ncu on the first version: 83 % of the shared-memory wavefront peak,
+// 7.3 wavefronts per 8-byte load): every lane address is a multiple of the pixel pitch, so 8-byte loads can at best
+// reach a 2-way conflict.  16-byte loads are conflict free when, per quarter warp (lanes g in {2k, 2k+1}, t = 0..3),
+// the eight 16-byte pieces fall into different bank groups: columns 2t give t*(Cb/4) mod 8 = {0,2,4,6} when Cb/8 is
+// odd, and consecutive contexts g, g+1 are consecutive ROWS of one window, one odd multiple of 16 bytes apart when
+// the staged width Wi is odd as well.
 //
 // Output: lanes hold (pixel, 4 channels) fragments, i.e. 8-byte pieces 2*C bytes apart -- written straight to
 // global memory that would be one 32-byte sector per lane.  They are staged in a shared-memory output tile
@@ -79,7 +86,7 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t a0, const
 // barrier keep them on the right side of the synchronisation points.
 __device__ __forceinline__ uint2 lds64m(const uint8_t* p) { return *reinterpret_cast<const uint2*>(p); }
 __device__ __forceinline__ uint4 lds128m(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
-__device__ __forceinline__ void sts64m(uint8_t* p, uint32_t x, uint32_t y) { *reinterpret_cast<uint2*>(p) = make_uint2(x, y); }
+__device__ __forceinline__ void sts128m(uint8_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
@@ -95,33 +102,37 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// A-fragment halves of one tile row: for chunk q and channel c, lo = pixels (2t, 2t+1), hi = pixels (2t+8, 2t+9)
-template <int NCH>
+// A-fragment halves of one tile row for 8 channels: lo = pixels (2t, 2t+1), hi = pixels (2t+8, 2t+9)
 struct RowFrag {
-    uint32_t lo[NCH][4];
-    uint32_t hi[NCH][4];
+    uint32_t lo[8];
+    uint32_t hi[8];
 };
 
-template <int NCH>
-__device__ __forceinline__ void load_row(RowFrag<NCH>& f, const uint8_t* addr, uint32_t pb) {
-#pragma unroll
-    for (int q = 0; q < NCH; ++q) {
-        const uint8_t* a = addr + (uint32_t)(16 * q) * pb;
-        const uint2 l0 = lds64m(a), l1 = lds64m(a + pb), l8 = lds64m(a + 8 * pb), l9 = lds64m(a + 9 * pb);
-        f.lo[q][0] = prmt(l0.x, l1.x, 0x5410); f.lo[q][1] = prmt(l0.x, l1.x, 0x7632);
-        f.lo[q][2] = prmt(l0.y, l1.y, 0x5410); f.lo[q][3] = prmt(l0.y, l1.y, 0x7632);
-        f.hi[q][0] = prmt(l8.x, l9.x, 0x5410); f.hi[q][1] = prmt(l8.x, l9.x, 0x7632);
-        f.hi[q][2] = prmt(l8.y, l9.y, 0x5410); f.hi[q][3] = prmt(l8.y, l9.y, 0x7632);
-    }
+// `vmask` bit j tells whether column j (offsets 0, 1, 8, 9) lies inside the staged row; the columns left of the
+// image (the convolution's zero padding) and right of the staged width read as zero.
+__device__ __forceinline__ void load_row(RowFrag& f, const uint8_t* a, uint32_t pb, uint32_t vmask) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 l0 = (vmask & 1u) ? lds128m(a) : z;
+    const uint4 l1 = (vmask & 2u) ? lds128m(a + pb) : z;
+    const uint4 l8 = (vmask & 4u) ? lds128m(a + 8 * pb) : z;
+    const uint4 l9 = (vmask & 8u) ? lds128m(a + 9 * pb) : z;
+    f.lo[0] = prmt(l0.x, l1.x, 0x5410); f.lo[1] = prmt(l0.x, l1.x, 0x7632);
+    f.lo[2] = prmt(l0.y, l1.y, 0x5410); f.lo[3] = prmt(l0.y, l1.y, 0x7632);
+    f.lo[4] = prmt(l0.z, l1.z, 0x5410); f.lo[5] = prmt(l0.z, l1.z, 0x7632);
+    f.lo[6] = prmt(l0.w, l1.w, 0x5410); f.lo[7] = prmt(l0.w, l1.w, 0x7632);
+    f.hi[0] = prmt(l8.x, l9.x, 0x5410); f.hi[1] = prmt(l8.x, l9.x, 0x7632);
+    f.hi[2] = prmt(l8.y, l9.y, 0x5410); f.hi[3] = prmt(l8.y, l9.y, 0x7632);
+    f.hi[4] = prmt(l8.z, l9.z, 0x5410); f.hi[5] = prmt(l8.z, l9.z, 0x7632);
+    f.hi[6] = prmt(l8.w, l9.w, 0x5410); f.hi[7] = prmt(l8.w, l9.w, 0x7632);
 }
 
-template <int K, int NCH>
+template <int K>
 __global__ void __launch_bounds__(DWM_THREADS, 1)
 dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                  const float* __restrict__ w_tc, __nv_bfloat16* __restrict__ y, const MmaPlan p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ MmaCtx cx;
-    constexpr int NT = 2 * NCH;                          // 8-wide output column groups per window
+    constexpr int NT = 2;                                // 8-wide output column groups per window
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* ring = smem_raw + (((raw + 127u) & ~127u) - raw);
     uint8_t* tab = ring + (size_t)p.stages * p.in_bytes;
@@ -136,13 +147,13 @@ dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tma_prefetch_desc(&tmY);
     }
     pdl_wait();                 // w_tc (a cast kernel's output) and the activations are valid from here on
-    // weight table: tab[cg][i][slot][4 ch] = packed (w[i][slot-1], w[i][slot]) as bf16 pairs, zero outside the filter
+    // weight table: tab[cg][i][slot][8 ch] = packed (w[i][slot-1], w[i][slot]) as bf16 pairs, zero outside the filter
     {
         uint32_t* t32 = reinterpret_cast<uint32_t*>(tab);
-        const int n = p.NCG * K * 8 * 4;
+        const int n = p.NCG * K * 8 * 8;
         for (int e = tid; e < n; e += DWM_THREADS) {
-            const int ch = e & 3, slot = (e >> 2) & 7, i = (e >> 5) % K, cg = (e >> 5) / K;
-            const int c = c_base + cg * 4 + ch;
+            const int ch = e & 7, slot = (e >> 3) & 7, i = (e >> 6) % K, cg = (e >> 6) / K;
+            const int c = c_base + cg * 8 + ch;
             float lo = 0.f, hi = 0.f;
             if (c < p.C) {
                 const int d0 = slot - 1, d1 = slot;
@@ -172,7 +183,7 @@ dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 const int s = n % p.stages;
                 const int3 c = tile_coord(n);
                 mbar_expect_tx(&cx.full[s], (uint32_t)(p.NF * p.Hi * p.Wi * p.Cb * 2));
-                tma_load_5d(ring + (size_t)s * p.in_bytes, &tmX, &cx.full[s], c_base, -p.p, c.z - p.p,
+                tma_load_5d(ring + (size_t)s * p.in_bytes, &tmX, &cx.full[s], c_base, 0, c.z - p.p,
                             p.src_first + c.y * p.NF, c.x);
             };
             for (int n = 0; n < my_tiles && n < p.stages; ++n) issue_load(n);
@@ -206,12 +217,25 @@ dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
 
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int win = g % p.NW, rowpair = g / p.NW;
+    // contexts g (h = 0) and g + 8 (h = 1): context m is row m % RP of window m / RP of the pass, so that the lane
+    // pairs (g, g+1) of a quarter warp read consecutive rows (bank-conflict free, see the file header)
+    int ctx_row[2], ctx_win[2], col0[2];
+    uint32_t vmask[2] = {0, 0};                          // which of its 4 columns exist in the staged row
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int m = g + 8 * h;
+        ctx_row[h] = m % p.RP; ctx_win[h] = m / p.RP;
+        col0[h] = ctx_win[h] * p.VW + 2 * t - p.p;      // first input column this lane reads (may be left of the image)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = col0[h] + (j & 1) + (j >> 1) * 8;
+            if (c >= 0 && c < p.Wi) vmask[h] |= 1u << j;
+        }
+    }
     // weight-table slots of this lane: b0 = P[e], b1 = P[e+8] with e = 2t - g (slot 7 holds zeros)
     const int e0 = 2 * t - g;
-    const uint32_t slot0 = (uint32_t)((e0 >= -1 && e0 <= K - 1) ? e0 + 1 : 7) * 16;
-    const uint32_t slot1 = (uint32_t)((e0 + 8 >= -1 && e0 + 8 <= K - 1) ? e0 + 9 : 7) * 16;
-    const int col0 = win * p.VW + 2 * t;                  // first input column (tile coordinates) this lane reads
+    const uint32_t slot0 = (uint32_t)((e0 >= -1 && e0 <= K - 1) ? e0 + 1 : 7) * 32;
+    const uint32_t slot1 = (uint32_t)((e0 + 8 >= -1 && e0 + 8 <= K - 1) ? e0 + 9 : 7) * 32;
     const int nfht = p.NF * p.Ht;
     const uint32_t row_bytes = (uint32_t)p.Wi * pb;
 
@@ -220,65 +244,69 @@ dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(&cx.full[s], (uint32_t)((n / p.stages) & 1));
         uint8_t* stage = ring + (size_t)s * p.in_bytes;
 
-        // A warp owns whole channel groups (4 channels = 8 bytes of every staged pixel) and walks their passes top
+        // A warp owns whole channel groups (8 channels = 16 bytes of every staged pixel) and walks their passes top
         // to bottom.  Outputs replace the inputs in place: output (r, c) goes where input (r, c) was.  Nobody else
         // touches this channel group's bytes, a pass has read everything it needs before it writes, and the rows it
         // overwrites (its own destination rows) are not read by the passes below it.
         for (int cg = warp; cg < p.NCG; cg += DWM_CWARPS) {
-            const uint8_t* wrow = tab + (uint32_t)(cg * K) * 128;
+            const uint8_t* wrow = tab + (uint32_t)(cg * K) * 256;
             for (int pass = 0; pass < p.NP; ++pass) {
-                const int vr0 = pass * p.RP + 2 * rowpair;            // destination row (frame-major) of context g
-                const bool valid = vr0 < nfht;
-                const int vrc = valid ? vr0 : 0;
-                const int f = vrc / p.Ht;
-                const int in_row0 = vrc + f * (K - 1);                // frame f starts at row f*Hi of the staged tile
-                uint8_t* arow = stage + (uint32_t)in_row0 * row_bytes + (uint32_t)col0 * pb + (uint32_t)cg * 8;
+                // destination rows (frame-major) of this lane's two contexts, and where they sit in the staged tile
+                bool valid[2];
+                const uint8_t* arow[2];
+                uint8_t* orow[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int vr = pass * p.RP + ctx_row[h];
+                    valid[h] = vr < nfht;
+                    const int vrc = valid[h] ? vr : 0;
+                    const int in_row = vrc + (vrc / p.Ht) * (K - 1);      // frame f starts at row f*Hi of the staged tile
+                    orow[h] = stage + (uint32_t)in_row * row_bytes + (uint32_t)cg * 16;
+                    arow[h] = orow[h] + col0[h] * (int)pb;
+                }
 
-                float acc[NT][4][4];
+                float acc[NT][8][4];
 #pragma unroll
                 for (int a = 0; a < NT; ++a)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
+                    for (int c = 0; c < 8; ++c)
 #pragma unroll
                         for (int r = 0; r < 4; ++r) acc[a][c][r] = 0.f;
 
-#pragma unroll
+#pragma unroll 1
                 for (int i = 0; i < K; ++i) {
-                    // context g reads tile row r+i, context g+8 (the next destination row) tile row r+1+i
-                    RowFrag<NCH> r0, r1;
-                    load_row<NCH>(r0, arow + (uint32_t)i * row_bytes, pb);
-                    load_row<NCH>(r1, arow + (uint32_t)(i + 1) * row_bytes, pb);
-                    const uint4 b0 = lds128m(wrow + (uint32_t)i * 128 + slot0);
-                    const uint4 b1 = lds128m(wrow + (uint32_t)i * 128 + slot1);
-                    const uint32_t b0c[4] = {b0.x, b0.y, b0.z, b0.w};
-                    const uint32_t b1c[4] = {b1.x, b1.y, b1.z, b1.w};
+                    RowFrag r0, r1;
+                    load_row(r0, arow[0] + (uint32_t)i * row_bytes, pb, vmask[0]);
+                    load_row(r1, arow[1] + (uint32_t)i * row_bytes, pb, vmask[1]);
+                    const uint4 b0a = lds128m(wrow + (uint32_t)i * 256 + slot0), b0b = lds128m(wrow + (uint32_t)i * 256 + slot0 + 16);
+                    const uint4 b1a = lds128m(wrow + (uint32_t)i * 256 + slot1), b1b = lds128m(wrow + (uint32_t)i * 256 + slot1 + 16);
+                    const uint32_t b0c[8] = {b0a.x, b0a.y, b0a.z, b0a.w, b0b.x, b0b.y, b0b.z, b0b.w};
+                    const uint32_t b1c[8] = {b1a.x, b1a.y, b1a.z, b1a.w, b1b.x, b1b.y, b1b.z, b1b.w};
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-#pragma unroll
-                        for (int q = 0; q < NCH; ++q) {
-                            const uint32_t a0 = r0.lo[q][c], a1 = r1.lo[q][c], a2 = r0.hi[q][c], a3 = r1.hi[q][c];
-                            mma_bf16(acc[2 * q][c], a0, a1, a2, a3, b0c[c], b1c[c]);          // outputs 16q + 0..7
-                            mma_bf16(acc[2 * q + 1][c], a0, a1, a2, a3, 0u, b0c[c]);          // outputs 16q + 8..15 (k >= 8)
-                            if (q > 0) mma_bf16(acc[2 * q - 1][c], a0, a1, a2, a3, b1c[c], 0u); // ... and their k >= 16 part
-                        }
+                    for (int c = 0; c < 8; ++c) {
+                        mma_bf16(acc[0][c], r0.lo[c], r1.lo[c], r0.hi[c], r1.hi[c], b0c[c], b1c[c]);   // outputs 0..7
+                        mma_bf16(acc[1][c], r0.lo[c], r1.lo[c], r0.hi[c], r1.hi[c], 0u, b0c[c]);       // outputs 8..15 (k >= 8)
                     }
                 }
                 __syncwarp();        // every lane has consumed its inputs (the MMAs are warp-wide): writes may start
 
-                // epilogue: (context h, column 8a + 2t + e) x 4 channels -> 8-byte pieces, in place
-                if (valid) {
-                    uint8_t* orow = stage + (uint32_t)in_row0 * row_bytes + (uint32_t)cg * 8;
+                // epilogue: (context h, column 8a + 2t + e) x 8 channels -> 16-byte pieces, in place
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (!valid[h]) continue;
 #pragma unroll
                     for (int a = 0; a < NT; ++a) {
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int wl = 8 * a + 2 * t + e;              // column inside the window
-                            const int col = win * p.VW + wl;
+                            const int col = ctx_win[h] * p.VW + wl;
                             if (wl < p.VW && col < p.Wo) {
-                                uint8_t* o0 = orow + (uint32_t)col * pb;
-                                sts64m(o0, pack_bf16x2(acc[a][0][e], acc[a][1][e]), pack_bf16x2(acc[a][2][e], acc[a][3][e]));
-                                sts64m(o0 + row_bytes, pack_bf16x2(acc[a][0][2 + e], acc[a][1][2 + e]),
-                                       pack_bf16x2(acc[a][2][2 + e], acc[a][3][2 + e]));
+                                uint4 o;
+                                o.x = pack_bf16x2(acc[a][0][2 * h + e], acc[a][1][2 * h + e]);
+                                o.y = pack_bf16x2(acc[a][2][2 * h + e], acc[a][3][2 * h + e]);
+                                o.z = pack_bf16x2(acc[a][4][2 * h + e], acc[a][5][2 * h + e]);
+                                o.w = pack_bf16x2(acc[a][6][2 * h + e], acc[a][7][2 * h + e]);
+                                sts128m(orow[h] + (uint32_t)col * pb, o);
                             }
                         }
                     }
@@ -302,33 +330,38 @@ static int make_map5_mma(CUtensorMap* tm, const void* base, int C, int W, int H,
     return make_tmap_bf16(tm, base, 5, dims, str, box, 0);
 }
 
-static bool plan_mma(MmaPlan& p, int B, int C, int To, int Ho, int Wo, int K, int NCH, int f_count) {
+// Tile planner.  Constraints that come from the hardware (measured, tools/tma_bench.cu and the bank structure):
+//  * shared-memory banks: lanes of a warp read 8-byte pieces of pixels (row g, column 2t + ...).  All strides are
+//    multiples of the pixel pitch, so the best case is a 2-way conflict, reached when Cb/8 and the staged width Wi
+//    are both odd; Cb = 96 with Wi = 16 is a 32-way conflict (measured: 3x slower than Cb = 120).
+//  * TMA unit: a box row is one staged pixel (Cb*2 bytes, rows are 2*C bytes apart in memory); one CTA gets a row
+//    every ~5 cycles up to ~140 bytes and ~28 bytes per cycle beyond, zero-filled rows included.
+//  * one tile spans the full width (in-place output; columns beyond the image are clipped by the store).
+// The score is useful bytes per estimated tile time = max(HBM time, TMA time, issue time).
+static bool plan_mma(MmaPlan& p, int B, int C, int To, int Ho, int Wo, int K, int f_count) {
     p.B = B; p.C = C; p.To = To; p.Ho = Ho; p.Wo = Wo; p.p = K / 2;
-    p.VW = 16 * NCH - (K - 1);
+    p.VW = 16 - (K - 1);
     const int nw = ceil_div(Wo, p.VW);
-    if (nw > 8) return false;                         // one tile spans the full width (in-place output, see the kernel)
+    if (nw > 8) return false;
     p.NW = nw <= 1 ? 1 : nw <= 2 ? 2 : nw <= 4 ? 4 : 8;
-    p.RP = 2 * (8 / p.NW);
-    p.Wi = (p.NW - 1) * p.VW + 16 * NCH;
+    p.RP = 16 / p.NW;
+    p.Wi = Wo | 1;                                    // odd staged width (one zero column more when Wo is even)
     if (p.Wi > 256) return false;
-    // The TMA unit pays per box row (= one staged pixel of Cb*2 bytes; tools/tma_bench.cu): under 128 bytes per row
-    // it cannot keep up with HBM, so narrow layers stay on the CUDA-core kernels of dwconv_tiled.cu.
-    if (C < 64) return false;
+    if (C < 64) return false;                         // box rows under 128 bytes: the CUDA-core kernels are faster
     double best = -1.0;
     int bCb = 0, bHt = 0, bNF = 0, bSt = 0;
     const int ho_even = (Ho + 1) / 2 * 2;
-    for (int nblk = ceil_div(C, 128); nblk <= ceil_div(C, 64); ++nblk) {
-        const int Cb = (ceil_div(C, nblk) + 7) / 8 * 8;
-        if (Cb < 64) break;
-        if ((nblk - 1) * Cb >= C) continue;                             // an empty last block
-        const int ncg = Cb / 4;
-        const int tab = ncg * K * 128;
+    const double item_clk = K == 5 ? 1600.0 : 1000.0;                    // one round: 8 items (8 channels each), one per warp
+    for (int Cb = 72; Cb <= 120; Cb += 16) {          // Cb/8 odd
+        const int nblk = ceil_div(C, Cb);
+        const int ncg = Cb / 8;
+        const int tab = ncg * K * 256;
+        const double pb = Cb * 2.0;
         for (int NF = 1; NF <= 4; ++NF) {
             if (NF > 1 && NF > f_count) break;
             for (int Ht = 2; Ht <= std::min(ho_even, 64); Ht += 2) {
                 if (NF > 1 && Ht < ho_even) continue;                    // several frames per tile only for whole planes
                 const int Hi = Ht + K - 1;
-                if (Hi > 256) break;
                 const long long inb = ((long long)NF * Hi * p.Wi * Cb * 2 + 127) / 128 * 128;
                 const long long left = DWM_SMEM_BUDGET - tab;
                 if (left < 2 * inb) continue;
@@ -336,23 +369,25 @@ static bool plan_mma(MmaPlan& p, int B, int C, int To, int Ho, int Wo, int K, in
                 const int NP = ceil_div(NF * Ht, p.RP);
                 const int th = ceil_div(Ho, Ht);
                 const double f_eff = (double)f_count / (ceil_div(f_count, NF) * NF);
-                const double useful = (double)Ho / th * NF * f_eff * Wo * ((double)C / nblk);
-                const double issued = (double)ceil_div(ncg, DWM_CWARPS) * DWM_CWARPS * 4.0 * NP * p.RP * p.NW * p.VW;
-                const double compute_eff = std::min(1.0, 1.6 * useful / issued);  // the math has headroom over the memory
-                const double halo = ((double)Ho / th * Wo) / ((double)Hi * p.Wi);   // useful share of the staged pixels
-                const double row_eff = std::min(1.0, Cb * 2 / 256.0);
-                const double score = compute_eff * (0.35 + 0.65 * halo) * (0.5 + 0.5 * row_eff) * (st >= 3 ? 1.0 : 0.9);
+                const double useful_px = (double)Ho / th * NF * f_eff * Wo;              // output pixels per tile
+                const double useful_bytes = useful_px * 2.0 * 2.0 * ((double)C / nblk);  // read once + written once
+                const double t_hbm = useful_bytes / 23.0;                                 // ~6.5 TB/s over 148 SMs
+                const double rows = (double)NF * (Hi + (NF > 1 ? Hi : Ht)) * p.Wi;        // loaded + stored box rows
+                const double t_tma = rows * std::max(5.0, pb / 28.0);
+                const double t_issue = (double)ceil_div(ncg, DWM_CWARPS) * NP * item_clk;
+                const double t = std::max(t_hbm, std::max(t_tma, t_issue)) * (st >= 3 ? 1.0 : 1.08) + 600.0;
+                const double score = useful_bytes / t;
                 if (score > best + 1e-9) { best = score; bCb = Cb; bHt = Ht; bNF = NF; bSt = st; }
             }
         }
     }
     if (best < 0) return false;
-    p.Cb = bCb; p.NCG = bCb / 4; p.nblk = ceil_div(C, bCb);
+    p.Cb = bCb; p.NCG = bCb / 8; p.nblk = ceil_div(C, bCb);
     p.Ht = bHt; p.NF = bNF; p.Hi = bHt + K - 1; p.stages = bSt;
     p.NP = ceil_div(p.NF * p.Ht, p.RP);
     p.tiles_h = ceil_div(Ho, p.Ht);
     p.in_bytes = (int)(((long long)p.NF * p.Hi * p.Wi * p.Cb * 2 + 127) / 128 * 128);
-    p.tab_bytes = p.NCG * K * 128;
+    p.tab_bytes = p.NCG * K * 256;
     return true;
 }
 
@@ -363,7 +398,7 @@ static bool dw_mma_enabled() {
 
 // dst[b][to][ho][wo][c] = sum_{i,j} src[b][to - pT][ho + i - p][wo + j - p][c] * w[(flip) i*K + j][c]
 // with src of size (Ts, Hs, Ws) == spatially (Ho, Wo); destination frames without a source frame are zeroed.
-template <int K, int NCH>
+template <int K>
 static bool launch_mma(const __nv_bfloat16* src, const float* w_tc, __nv_bfloat16* dst, int B, int C, int Ts, int To, int Ho,
                        int Wo, int pT, int flip, cudaStream_t st) {
     MmaPlan p{};
@@ -376,7 +411,7 @@ static bool launch_mma(const __nv_bfloat16* src, const float* w_tc, __nv_bfloat1
         else { if (p.nzf >= DWM_MAX_ZF || f > 255) return false; p.zf[p.nzf++] = (unsigned char)f; }
     }
     if (count == 0) return false;
-    if (!plan_mma(p, B, C, To, Ho, Wo, K, NCH, count)) return false;
+    if (!plan_mma(p, B, C, To, Ho, Wo, K, count)) return false;
     p.f_first = first; p.f_count = count; p.src_first = first - pT;
     p.tiles_f = ceil_div(count, p.NF);
     p.ntiles = (long long)B * p.tiles_f * p.tiles_h;
@@ -388,12 +423,12 @@ static bool launch_mma(const __nv_bfloat16* src, const float* w_tc, __nv_bfloat1
     // several frames per tile, the staged frame pitch Hi (rows >= Ho clipped: such tiles cover whole planes).
     if (make_map5_mma(&tmy, dst, C, Wo, Ho, To, B, p.Cb, p.Wi, p.NF > 1 ? p.Hi : p.Ht, p.NF) != PB_OK) return false;
     static unsigned long long once = 0;
-    if (ensure_dyn_smem(dw_s1_mma_kernel<K, NCH>, 226 * 1024, &once) != cudaSuccess) return false;
+    if (ensure_dyn_smem(dw_s1_mma_kernel<K>, 226 * 1024, &once) != cudaSuccess) return false;
     int ctas = std::max(1, 148 / p.nblk);
     ctas = (int)std::min<long long>(ctas, p.ntiles);
     if (p.stages > DWM_MAX_STAGES) p.stages = DWM_MAX_STAGES;
     const size_t smem = (size_t)p.stages * p.in_bytes + p.tab_bytes + 128;
-    (void)launch_pdl(dw_s1_mma_kernel<K, NCH>, dim3(ctas, p.nblk), dim3(DWM_THREADS), smem, st, tmx, tmy, w_tc, dst, p);
+    (void)launch_pdl(dw_s1_mma_kernel<K>, dim3(ctas, p.nblk), dim3(DWM_THREADS), smem, st, tmx, tmy, w_tc, dst, p);
     return true;
 }
 
@@ -405,22 +440,16 @@ static bool mma_class(const DwDims& d) {
 bool dw_fwd_mma(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y, const DwDims& d, cudaStream_t st) {
     if (!dw_mma_enabled() || !mma_class(d)) return false;
     if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0) return false;
-    const bool one = d.W + d.kW - 1 <= 16;
-    if (d.kH == 3) return one ? launch_mma<3, 1>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st)
-                              : launch_mma<3, 2>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st);
-    return one ? launch_mma<5, 1>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st)
-               : launch_mma<5, 2>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st);
+    return d.kH == 3 ? launch_mma<3>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st)
+                     : launch_mma<5>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st);
 }
 
 // stride-1 input gradient == correlation of dy with the flipped filter: dx[t] reads dy[t + pT]
 bool dw_dgrad_mma(const __nv_bfloat16* dy, const float* w_tc, __nv_bfloat16* dx, const DwDims& d, cudaStream_t st) {
     if (!dw_mma_enabled() || !mma_class(d)) return false;
     if (((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) != 0) return false;
-    const bool one = d.W + d.kW - 1 <= 16;
-    if (d.kH == 3) return one ? launch_mma<3, 1>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st)
-                              : launch_mma<3, 2>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st);
-    return one ? launch_mma<5, 1>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st)
-               : launch_mma<5, 2>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st);
+    return d.kH == 3 ? launch_mma<3>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st)
+                     : launch_mma<5>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st);
 }
 
 }  // namespace pb

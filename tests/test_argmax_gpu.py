@@ -3,7 +3,11 @@
 tests/golden/make_trained.py trained the synthetic checkpoints with the REFERENCE modules on a separable two-class
 task and stored the reference's own eval logits of 96 held-out clips.  Both classes are predicted and the margins
 are large against bf16 noise, so "argmax identical" is a real statement here (the seeded checkpoints of the other
-tests predict one class for every clip)."""
+tests predict one class for every clip).
+
+MobileNetLarge3D and MobileNetSmall3D only: MoViNetA2 did not get off ln 2 within 450 end-to-end CPU steps, and the
+pooled features of its synthetic checkpoint are effectively rank one on these clips (a closed-form fit of the head
+reaches 55 %), so no two-sided MoViNet fixture exists; its parity rests on the golden / train-step / stream tests."""
 import os
 
 import pytest
@@ -25,7 +29,7 @@ def _load(model):
     return fx, state
 
 
-@pytest.mark.parametrize("model", MODEL_NAMES)
+@pytest.mark.parametrize("model", ["MobileNetLarge3D", "MobileNetSmall3D"])
 def test_argmax_identical_on_trained_checkpoint(model):
     import picklebot_b200 as pb
     fx, state = _load(model)

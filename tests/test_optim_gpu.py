@@ -106,8 +106,8 @@ def test_model_with_adamw_eager_steps_follow_the_optimizer():
         m.load_state_dict(synthetic_checkpoint("MobileNetLarge3D"))
         m = m.cuda().train()
         models.append(m)
-        opts.append(AdamW(m.parameters(), lr=1e-2, weight_decay=1e-2) if kind == "ours"
-                    else torch.optim.AdamW(m.parameters(), lr=1e-2, weight_decay=1e-2))
+        opts.append(AdamW(m.parameters(), lr=1e-3, weight_decay=1e-2) if kind == "ours"
+                    else torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-2))
     w0 = models[0].block3[1].depthwise_conv.weight.detach().clone()
     losses = [[], []]
     for step in range(3):
@@ -118,10 +118,12 @@ def test_model_with_adamw_eager_steps_follow_the_optimizer():
             loss.backward()
             opt.step()
             losses[j].append(float(loss))
-    # lr 1e-2 moves every weight by ~1e-2 per step: with stale shadow copies the second and third losses differ grossly
-    assert float((models[0].block3[1].depthwise_conv.weight - w0).abs().max()) > 5e-3
+    # Adam moves every weight by ~lr per step: with stale shadow copies of the conv weights the second and third
+    # losses would be those of the initial convolutions
+    assert float((models[0].block3[1].depthwise_conv.weight - w0).abs().max()) > 1e-3
+    assert abs(losses[0][0] - losses[0][2]) > 0.05, losses                 # the steps did change the function
     for a, b in zip(losses[0], losses[1]):
-        assert abs(a - b) < 2e-2 * max(1.0, abs(b)), (losses[0], losses[1])
+        assert abs(a - b) < 5e-2 * max(1.0, abs(b)), (losses[0], losses[1])
     pa, pb_ = dict(models[0].named_parameters()), dict(models[1].named_parameters())
     flat_a = torch.cat([pa[k].detach().flatten() for k in pa])
     flat_b = torch.cat([pb_[k].detach().flatten() for k in pa])
