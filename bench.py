@@ -378,7 +378,7 @@ def main():
     else:
         from picklebot_b200.optim import AdamW          # one pb_adamw_step launch over all ~170 tensors
         opt = AdamW(model.parameters(), lr=3e-4, weight_decay=5e-4)
-    use_graph = not args.no_graphs and args.dp == "buckets" and mode != "stream"
+    use_graph = not args.no_graphs and args.dp == "buckets" and mode != "stream"      # (stream: GraphedStream below)
     from picklebot_b200 import loss as pbloss               # cross-entropy + accuracy count in one kernel (pb_ce_loss)
 
     # synthetic uint8 clips: this rank's shard of each global batch, distinct per micro-batch
@@ -389,6 +389,10 @@ def main():
     # ~370 launches from Python costs the host ~11 ms per 14 ms of GPU work, which starves the GPUs once eight
     # processes share the box's cores); gradients accumulate in place, the exchange runs after the last replay.
     gstep = gfwd = None
+    gstream = None
+    if mode == "stream" and not args.no_graphs:
+        from picklebot_b200.graph import GraphedStream
+        gstream = GraphedStream(model, clips[0][:, :cfg["chunk"]].permute(0, 4, 1, 2, 3))
     if use_graph and not train:
         from picklebot_b200.graph import GraphedForward
         gfwd = GraphedForward(model, clips[0].permute(0, 4, 1, 2, 3))
@@ -408,9 +412,15 @@ def main():
         else:
             torch._foreach_zero_(grad_list)     # the graph accumulates into these very tensors
 
-    def stream_clip(x_u8):
+    def stream_clip(x_u8, eager=False):
         """One batch of long clips through the causal streaming path, chunk by chunk; the stream state (tail frames
         of every temporal conv, cumulative squeeze-excite / head sums) lives on the device between the calls."""
+        if gstream is not None and not eager:
+            gstream.reset()
+            logits = None
+            for t0 in range(0, clip_shape[0], cfg["chunk"]):
+                logits = gstream(x_u8[:, t0:t0 + cfg["chunk"]].permute(0, 4, 1, 2, 3))
+            return logits
         state = model.init_stream_state()
         logits = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -420,7 +430,7 @@ def main():
 
     def micro_step(x_u8, y, sync_grads, eager=False):
         if mode == "stream":
-            return stream_clip(x_u8)
+            return stream_clip(x_u8, eager)
         if mode == "infer":
             if gfwd is not None and not eager:
                 return gfwd(x_u8.permute(0, 4, 1, 2, 3))
@@ -484,6 +494,8 @@ def main():
     launches = _lib.launch_count() - n0
     if gstep is not None or gfwd is not None:   # replays launch the captured kernels without passing the C ABI
         launches += args.steps * accum * (gstep or gfwd).launches
+    if gstream is not None:
+        launches += args.steps * accum * (clip_shape[0] // cfg["chunk"]) * gstream.launches
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = args.global_batch / (ms_per_step / 1000.0)
@@ -626,8 +638,10 @@ def main():
             conf["launch"] = ("eval forward of a micro-batch captured once in a CUDA graph (picklebot_b200.graph."
                               "GraphedForward) and replayed" if gfwd is not None else "eager")
         else:
-            conf["launch"] = (f"eager: {clip_shape[0] // cfg['chunk']} forward_stream calls per clip batch, stream state "
-                              f"resident on the device between calls")
+            conf["launch"] = (f"{clip_shape[0] // cfg['chunk']} forward_stream chunk steps per clip batch, " +
+                              ("one captured CUDA graph replayed per chunk (picklebot_b200.graph.GraphedStream)"
+                               if gstream is not None else "eager") +
+                              "; stream buffers and cumulative pooling state resident in HBM, updated in place")
         line = {
             "metric": cfg["metric"], "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,

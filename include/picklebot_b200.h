@@ -170,6 +170,11 @@ int pb_bn_act_bwd_apply(const void* dout, int dout_bcast, const void* z, const f
  * classifiers (mobilenet.py:186, 252; movinet.py:147).
  * ---------------------------------------------------------------------------------------------- */
 int pb_pool_fwd(const void* x, int dtype, int B, long long R, int C, float* mean, pb_stream_t stream);
+/* Streaming mode (MoViNet stream state, BASELINE config 4): global pools become cumulative means over all frames
+ * seen so far.  sum[b][c] += chunk_mean[b][c] * R;  rows[0] += R;  mean_out = sum / rows.  `sum` (fp32 [B][C]) and
+ * `rows` (int64 device scalar) are stream state resident in HBM between chunk calls (zero them to start a clip). */
+int pb_stream_pool_update(const float* chunk_mean, long long R, float* sum, long long* rows, float* mean_out,
+                          int B, int C, pb_stream_t stream);
 /* Classifier-head linear layers (nn.Linear, mobilenet.py:184-190,250-256; movinet.py:146-154), fp32:
  * Y[b][n] = bias[n] + sum_k X[b][k] W[n][k]   and   dX[b][k] = scale * sum_n dY[b][n] W[n][k]. */
 int pb_fc_fwd(const float* X, const float* W, const float* bias, float* Y, int B, int N, int K, pb_stream_t stream);

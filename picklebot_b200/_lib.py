@@ -40,6 +40,7 @@ SIGNATURES = {
     "pb_bn_bwd_finalize": "plipppip",
     "pb_bn_act_bwd_apply": "pipppppppp" + "iiliifp",
     "pb_pool_fwd": "piilipp",
+    "pb_stream_pool_update": "plpppiip",
     "pb_fc_fwd": "ppppiiip",
     "pb_fc_dgrad": "pppiiifp",
     "pb_se_fc_fwd": "pppppppiiip",

@@ -263,11 +263,22 @@ extern "C" int pb_stream_dwconv3d_fwd(const void* x, const void* stream_buf, con
     PB_REQUIRE(kT == 1 || (stream_buf && stream_buf_out), "stream_dwconv3d: stream buffers required for kT>1");
     PB_REQUIRE(stream_buf_out != stream_buf || kT - 1 <= T_, "stream_dwconv3d: in-place tail update needs T >= kT-1");
     cudaStream_t st = (cudaStream_t)stream;
+    bool tiled = false;
+    if (dtype == PB_BF16 && kT == 1) {      // no temporal taps: the stateless (1,k,k) kernels serve the chunk
+        DwDims d1 = d;
+        d1.pT = 0;
+        tiled = dw_fwd_tiled<__nv_bfloat16>((const __nv_bfloat16*)x, w_tc, (__nv_bfloat16*)y, d1, st);
+    }
+    if (dtype == PB_BF16 && kT > 1)
+        tiled = dw_stream_fwd_tiled((const __nv_bfloat16*)x, (const __nv_bfloat16*)stream_buf, w_tc, (__nv_bfloat16*)y, d, st);
+    if (tiled) { PB_CHECK_LAUNCH("dw_stream_fwd_tiled"); count_path(PB_PATH_DW_STREAM_TMA); }
     PB_DISPATCH_DTYPE(dtype, {
-        long long total = (long long)B * T_ * Ho * Wo * (C / 8);
-        dw_fwd_generic<T, true><<<ceil_div(total, 256), 256, 0, st>>>((const T*)x, (const T*)stream_buf, w_tc, (T*)y, d, total);
-        PB_CHECK_LAUNCH("dw_fwd_stream");
-        count_path(PB_PATH_DW_STREAM_GENERIC);
+        if (!tiled) {
+            long long total = (long long)B * T_ * Ho * Wo * (C / 8);
+            dw_fwd_generic<T, true><<<ceil_div(total, 256), 256, 0, st>>>((const T*)x, (const T*)stream_buf, w_tc, (T*)y, d, total);
+            PB_CHECK_LAUNCH("dw_fwd_stream");
+            count_path(PB_PATH_DW_STREAM_GENERIC);
+        }
         if (kT > 1) {
             long long fe8 = (long long)H * W * (C / 8);
             long long n = (long long)B * (kT - 1) * fe8;

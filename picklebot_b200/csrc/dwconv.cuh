@@ -20,4 +20,8 @@ template <typename T> bool dw_wgrad_tiled(const T* x, const T* dy, float* dw_tc,
 bool dw_fwd_mma(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y, const DwDims& d, cudaStream_t st);
 bool dw_dgrad_mma(const __nv_bfloat16* dy, const float* w_tc, __nv_bfloat16* dx, const DwDims& d, cudaStream_t st);
 
+// TMA-tiled causal streaming forward for the (kT,3,3) MoViNet layers (dwconv_tiled.cu); false = not handled.
+bool dw_stream_fwd_tiled(const __nv_bfloat16* x, const __nv_bfloat16* sbuf, const float* w_tc, __nv_bfloat16* y,
+                         const DwDims& d, cudaStream_t st);
+
 }  // namespace pb

@@ -48,8 +48,8 @@ using namespace tc;
 
 constexpr int DWM_CWARPS = 8;                       // compute warps
 constexpr int DWM_COMPUTE = DWM_CWARPS * 32;
-constexpr int DWM_THREADS = DWM_COMPUTE + 32;       // + one warp that drives the TMA unit (loads and stores)
 constexpr int DWM_MAX_STAGES = 4;
+constexpr int DWM_THREADS = DWM_COMPUTE + 32 * DWM_MAX_STAGES;   // + one warp per ring stage that drives the TMA unit
 constexpr int DWM_MAX_ZF = 64;
 constexpr int DWM_SMEM_BUDGET = 216 * 1024;
 
@@ -74,6 +74,24 @@ struct MmaCtx {
     uint64_t full[DWM_MAX_STAGES];      // TMA load of the stage has landed
     uint64_t done[DWM_MAX_STAGES];      // all compute warps have finished the tile (outputs written in place)
 };
+
+// mbarrier wait that lets the hardware park the thread (suspend-time hint, ns) instead of re-issuing try_wait in a
+// tight loop: the waiting TMA lanes must not steal issue slots from the compute warps of this 1-CTA-per-SM kernel.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+        if (++spins > (1u << 22)) __trap();
+    }
+}
 
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2,
                                          const uint32_t a3, const uint32_t b0, const uint32_t b1) {
@@ -108,14 +126,11 @@ struct RowFrag {
     uint32_t hi[8];
 };
 
-// `vmask` bit j tells whether column j (offsets 0, 1, 8, 9) lies inside the staged row; the columns left of the
-// image (the convolution's zero padding) and right of the staged width read as zero.
-__device__ __forceinline__ void load_row(RowFrag& f, const uint8_t* a, uint32_t pb, uint32_t vmask) {
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const uint4 l0 = (vmask & 1u) ? lds128m(a) : z;
-    const uint4 l1 = (vmask & 2u) ? lds128m(a + pb) : z;
-    const uint4 l8 = (vmask & 4u) ? lds128m(a + 8 * pb) : z;
-    const uint4 l9 = (vmask & 8u) ? lds128m(a + 9 * pb) : z;
+// `a` = start of this lane's context row, off[j] = byte offsets of its four columns (window columns 2t, 2t+1, 2t+8,
+// 2t+9 shifted by the padding).  Columns outside the image read the staged zero column Wo instead (the TMA unit
+// filled it): no predicates in the inner loop.
+__device__ __forceinline__ void load_row(RowFrag& f, const uint8_t* a, const uint32_t (&off)[4]) {
+    const uint4 l0 = lds128m(a + off[0]), l1 = lds128m(a + off[1]), l8 = lds128m(a + off[2]), l9 = lds128m(a + off[3]);
     f.lo[0] = prmt(l0.x, l1.x, 0x5410); f.lo[1] = prmt(l0.x, l1.x, 0x7632);
     f.lo[2] = prmt(l0.y, l1.y, 0x5410); f.lo[3] = prmt(l0.y, l1.y, 0x7632);
     f.lo[4] = prmt(l0.z, l1.z, 0x5410); f.lo[5] = prmt(l0.z, l1.z, 0x7632);
@@ -167,10 +182,12 @@ dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int my_tiles = p.ntiles > blockIdx.x ? (int)((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
     if (tid >= DWM_COMPUTE) {
-        // ---- TMA warp: one lane.  Loads fill the ring; when the compute warps are done with a tile (its outputs
-        // now sit in the stage, at the positions of the top-left input pixels) the tile is stored from there and,
-        // once the store has read the stage, the stage is refilled with the tile `stages` ahead.
-        if (tid == DWM_COMPUTE) {
+        // ---- TMA warps, one lane each, one per ring stage: stage s serves tiles s, s + stages, ...  When the compute
+        // warps are done with a tile (its outputs now sit in the stage, at the positions of the top-left input
+        // pixels) it is stored from there and, once the store has READ the stage, the stage is refilled.  A stage
+        // per warp keeps that wait off the other stages' critical path (bulk async-groups are per thread).
+        const int s = (tid - DWM_COMPUTE) >> 5;
+        if ((tid & 31) == 0 && s < p.stages) {
             auto tile_coord = [&](int n) {
                 unsigned t = (unsigned)blockIdx.x + (unsigned)n * gridDim.x;      // ntiles < 2^31 (checked on the host)
                 int3 c;
@@ -179,22 +196,21 @@ dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 c.x = (int)(t / p.tiles_f);
                 return c;
             };
+            uint8_t* stage = ring + (size_t)s * p.in_bytes;
             auto issue_load = [&](int n) {
-                const int s = n % p.stages;
                 const int3 c = tile_coord(n);
                 mbar_expect_tx(&cx.full[s], (uint32_t)(p.NF * p.Hi * p.Wi * p.Cb * 2));
-                tma_load_5d(ring + (size_t)s * p.in_bytes, &tmX, &cx.full[s], c_base, 0, c.z - p.p,
-                            p.src_first + c.y * p.NF, c.x);
+                tma_load_5d(stage, &tmX, &cx.full[s], c_base, 0, c.z - p.p, p.src_first + c.y * p.NF, c.x);
             };
-            for (int n = 0; n < my_tiles && n < p.stages; ++n) issue_load(n);
-            for (int n = 0; n < my_tiles; ++n) {
-                const int s = n % p.stages;
-                mbar_wait(&cx.done[s], (uint32_t)((n / p.stages) & 1));
+            if (s < my_tiles) issue_load(s);
+            uint32_t phase = 0;
+            for (int n = s; n < my_tiles; n += p.stages, phase ^= 1) {
+                mbar_wait_parked(&cx.done[s], phase);
                 const int3 c = tile_coord(n);
-                tma_store_5d(&tmY, ring + (size_t)s * p.in_bytes, c_base, 0, c.z, p.f_first + c.y * p.NF, c.x);
+                tma_store_5d(&tmY, stage, c_base, 0, c.z, p.f_first + c.y * p.NF, c.x);
                 bulk_commit();
                 if (n + p.stages < my_tiles) {
-                    bulk_wait_read0();                      // the store has read the stage: it may be overwritten
+                    bulk_wait_read0();                      // the stores have read the stage: it may be overwritten
                     issue_load(n + p.stages);
                 }
             }
@@ -219,18 +235,29 @@ dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     // contexts g (h = 0) and g + 8 (h = 1): context m is row m % RP of window m / RP of the pass, so that the lane
     // pairs (g, g+1) of a quarter warp read consecutive rows (bank-conflict free, see the file header)
-    int ctx_row[2], ctx_win[2], col0[2];
-    uint32_t vmask[2] = {0, 0};                          // which of its 4 columns exist in the staged row
+    int ctx_row[2];
+    uint32_t off[2][4];                                  // byte offsets of the four input columns this lane reads
+    uint32_t ocol[2];                                    // byte offset of output column 2t of the lane's window
+    uint32_t omask[2] = {0, 0};                          // bit (2a + e): output column 8a + 2t + e exists
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int m = g + 8 * h;
-        ctx_row[h] = m % p.RP; ctx_win[h] = m / p.RP;
-        col0[h] = ctx_win[h] * p.VW + 2 * t - p.p;      // first input column this lane reads (may be left of the image)
+        ctx_row[h] = m % p.RP;
+        const int win = m / p.RP;
+        const int c0 = win * p.VW + 2 * t - p.p;         // first input column (may be left of the image)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int c = col0[h] + (j & 1) + (j >> 1) * 8;
-            if (c >= 0 && c < p.Wi) vmask[h] |= 1u << j;
+            const int c = c0 + (j & 1) + (j >> 1) * 8;
+            off[h][j] = (uint32_t)((c >= 0 && c < p.Wo) ? c : p.Wo) * pb;      // column Wo is staged as zeros
         }
+        ocol[h] = (uint32_t)(win * p.VW + 2 * t) * pb;
+#pragma unroll
+        for (int a = 0; a < NT; ++a)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int wl = 8 * a + 2 * t + e;
+                if (wl < p.VW && win * p.VW + wl < p.Wo) omask[h] |= 1u << (2 * a + e);
+            }
     }
     // weight-table slots of this lane: b0 = P[e], b1 = P[e+8] with e = 2t - g (slot 7 holds zeros)
     const int e0 = 2 * t - g;
@@ -241,7 +268,7 @@ dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
     for (int n = 0; n < my_tiles; ++n) {
         const int s = n % p.stages;
-        mbar_wait(&cx.full[s], (uint32_t)((n / p.stages) & 1));
+        mbar_wait_parked(&cx.full[s], (uint32_t)((n / p.stages) & 1));
         uint8_t* stage = ring + (size_t)s * p.in_bytes;
 
         // A warp owns whole channel groups (8 channels = 16 bytes of every staged pixel) and walks their passes top
@@ -253,16 +280,14 @@ dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int pass = 0; pass < p.NP; ++pass) {
                 // destination rows (frame-major) of this lane's two contexts, and where they sit in the staged tile
                 bool valid[2];
-                const uint8_t* arow[2];
                 uint8_t* orow[2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int vr = pass * p.RP + ctx_row[h];
                     valid[h] = vr < nfht;
                     const int vrc = valid[h] ? vr : 0;
-                    const int in_row = vrc + (vrc / p.Ht) * (K - 1);      // frame f starts at row f*Hi of the staged tile
-                    orow[h] = stage + (uint32_t)in_row * row_bytes + (uint32_t)cg * 16;
-                    arow[h] = orow[h] + col0[h] * (int)pb;
+                    const int f = p.NF == 1 ? 0 : vrc / p.Ht;
+                    orow[h] = stage + (uint32_t)(vrc + f * (K - 1)) * row_bytes + (uint32_t)cg * 16;   // frame f starts at row f*Hi
                 }
 
                 float acc[NT][8][4];
@@ -276,8 +301,8 @@ dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll 1
                 for (int i = 0; i < K; ++i) {
                     RowFrag r0, r1;
-                    load_row(r0, arow[0] + (uint32_t)i * row_bytes, pb, vmask[0]);
-                    load_row(r1, arow[1] + (uint32_t)i * row_bytes, pb, vmask[1]);
+                    load_row(r0, orow[0] + (uint32_t)i * row_bytes, off[0]);
+                    load_row(r1, orow[1] + (uint32_t)i * row_bytes, off[1]);
                     const uint4 b0a = lds128m(wrow + (uint32_t)i * 256 + slot0), b0b = lds128m(wrow + (uint32_t)i * 256 + slot0 + 16);
                     const uint4 b1a = lds128m(wrow + (uint32_t)i * 256 + slot1), b1b = lds128m(wrow + (uint32_t)i * 256 + slot1 + 16);
                     const uint32_t b0c[8] = {b0a.x, b0a.y, b0a.z, b0a.w, b0b.x, b0b.y, b0b.z, b0b.w};
@@ -294,19 +319,18 @@ dw_s1_mma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     if (!valid[h]) continue;
+                    uint8_t* o0 = orow[h] + ocol[h];
 #pragma unroll
                     for (int a = 0; a < NT; ++a) {
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const int wl = 8 * a + 2 * t + e;              // column inside the window
-                            const int col = ctx_win[h] * p.VW + wl;
-                            if (wl < p.VW && col < p.Wo) {
+                            if ((omask[h] >> (2 * a + e)) & 1u) {
                                 uint4 o;
                                 o.x = pack_bf16x2(acc[a][0][2 * h + e], acc[a][1][2 * h + e]);
                                 o.y = pack_bf16x2(acc[a][2][2 * h + e], acc[a][3][2 * h + e]);
                                 o.z = pack_bf16x2(acc[a][4][2 * h + e], acc[a][5][2 * h + e]);
                                 o.w = pack_bf16x2(acc[a][6][2 * h + e], acc[a][7][2 * h + e]);
-                                sts128m(orow[h] + (uint32_t)col * pb, o);
+                                sts128m(o0 + (uint32_t)(8 * a + e) * pb, o);
                             }
                         }
                     }
@@ -345,22 +369,21 @@ static bool plan_mma(MmaPlan& p, int B, int C, int To, int Ho, int Wo, int K, in
     if (nw > 8) return false;
     p.NW = nw <= 1 ? 1 : nw <= 2 ? 2 : nw <= 4 ? 4 : 8;
     p.RP = 16 / p.NW;
-    p.Wi = Wo | 1;                                    // odd staged width (one zero column more when Wo is even)
+    p.Wi = Wo + 1 + (Wo & 1);                         // odd staged width with at least one zero column right of the image
     if (p.Wi > 256) return false;
     if (C < 64) return false;                         // box rows under 128 bytes: the CUDA-core kernels are faster
     double best = -1.0;
     int bCb = 0, bHt = 0, bNF = 0, bSt = 0;
-    const int ho_even = (Ho + 1) / 2 * 2;
-    const double item_clk = K == 5 ? 1600.0 : 1000.0;                    // one round: 8 items (8 channels each), one per warp
     for (int Cb = 72; Cb <= 120; Cb += 16) {          // Cb/8 odd
         const int nblk = ceil_div(C, Cb);
         const int ncg = Cb / 8;
         const int tab = ncg * K * 256;
-        const double pb = Cb * 2.0;
+        const double ch_eff = (double)C / (nblk * Cb);                   // real channels per staged channel
+        const double warp_eff = (double)ncg / (ceil_div(ncg, DWM_CWARPS) * DWM_CWARPS);
         for (int NF = 1; NF <= 4; ++NF) {
             if (NF > 1 && NF > f_count) break;
-            for (int Ht = 2; Ht <= std::min(ho_even, 64); Ht += 2) {
-                if (NF > 1 && Ht < ho_even) continue;                    // several frames per tile only for whole planes
+            for (int Ht = 1; Ht <= std::min(Ho, 64); ++Ht) {
+                if (NF > 1 && Ht < Ho) continue;                         // several frames per tile only for whole planes
                 const int Hi = Ht + K - 1;
                 const long long inb = ((long long)NF * Hi * p.Wi * Cb * 2 + 127) / 128 * 128;
                 const long long left = DWM_SMEM_BUDGET - tab;
@@ -369,14 +392,13 @@ static bool plan_mma(MmaPlan& p, int B, int C, int To, int Ho, int Wo, int K, in
                 const int NP = ceil_div(NF * Ht, p.RP);
                 const int th = ceil_div(Ho, Ht);
                 const double f_eff = (double)f_count / (ceil_div(f_count, NF) * NF);
-                const double useful_px = (double)Ho / th * NF * f_eff * Wo;              // output pixels per tile
-                const double useful_bytes = useful_px * 2.0 * 2.0 * ((double)C / nblk);  // read once + written once
-                const double t_hbm = useful_bytes / 23.0;                                 // ~6.5 TB/s over 148 SMs
-                const double rows = (double)NF * (Hi + (NF > 1 ? Hi : Ht)) * p.Wi;        // loaded + stored box rows
-                const double t_tma = rows * std::max(5.0, pb / 28.0);
-                const double t_issue = (double)ceil_div(ncg, DWM_CWARPS) * NP * item_clk;
-                const double t = std::max(t_hbm, std::max(t_tma, t_issue)) * (st >= 3 ? 1.0 : 1.08) + 600.0;
-                const double score = useful_bytes / t;
+                const double ctx_eff = ((double)Ho / th * NF * f_eff) / (NP * p.RP) * ((double)Wo / (p.NW * p.VW));
+                const double halo_eff = ((double)Ho / th * 2.0) / (Hi + (NF > 1 ? Hi : Ht));   // useful share of the loaded + stored rows
+                // the math has headroom over the memory system (ncu: issue slots ~40 % busy at 4 TB/s), so its
+                // efficiencies enter damped; a third ring stage hides the store -> refill turnaround
+                const double row_pref = 0.7 + 0.3 * std::min(120.0, (double)C / nblk) / 120.0;   // long box rows
+                const double score = (0.2 + 0.8 * ch_eff) * (0.4 + 0.6 * ctx_eff * warp_eff) * halo_eff * row_pref *
+                                     (st >= 3 ? 1.0 : 0.85);
                 if (score > best + 1e-9) { best = score; bCb = Cb; bHt = Ht; bNF = NF; bSt = st; }
             }
         }
@@ -391,10 +413,6 @@ static bool plan_mma(MmaPlan& p, int B, int C, int To, int Ho, int Wo, int K, in
     return true;
 }
 
-static bool dw_mma_enabled() {
-    static const bool on = [] { const char* e = getenv("PB_DW_MMA"); return !(e && e[0] == '0'); }();
-    return on;
-}
 
 // dst[b][to][ho][wo][c] = sum_{i,j} src[b][to - pT][ho + i - p][wo + j - p][c] * w[(flip) i*K + j][c]
 // with src of size (Ts, Hs, Ws) == spatially (Ho, Wo); destination frames without a source frame are zeroed.
@@ -420,7 +438,8 @@ static bool launch_mma(const __nv_bfloat16* src, const float* w_tc, __nv_bfloat1
     CUtensorMap tmx, tmy;
     if (make_map5_mma(&tmx, src, C, Wo, Ho, Ts, B, p.Cb, p.Wi, p.Hi, p.NF) != PB_OK) return false;
     // The store reads the stage itself: full staged width (columns >= Wo are clipped by the TMA unit) and, with
-    // several frames per tile, the staged frame pitch Hi (rows >= Ho clipped: such tiles cover whole planes).
+    // several frames per tile, the staged frame pitch Hi (rows >= Ho clipped: such tiles cover whole planes; a
+    // store per frame would need frame offsets that are multiples of 128 bytes).
     if (make_map5_mma(&tmy, dst, C, Wo, Ho, To, B, p.Cb, p.Wi, p.NF > 1 ? p.Hi : p.Ht, p.NF) != PB_OK) return false;
     static unsigned long long once = 0;
     if (ensure_dyn_smem(dw_s1_mma_kernel<K>, 226 * 1024, &once) != cudaSuccess) return false;
@@ -432,13 +451,24 @@ static bool launch_mma(const __nv_bfloat16* src, const float* w_tc, __nv_bfloat1
     return true;
 }
 
+// PB_DW_MMA=1 forces this kernel for every shape it supports (tests, experiments), =0 disables it; by default it
+// serves the shapes where it measured faster than the CUDA-core kernels of dwconv_tiled.cu on B200
+// (profiles/r02_dw_microbench.txt): 3x3 layers on 14x14 planes with >= 400 channels (MobileNetLarge3D block4.4 /
+// block4.5: 4.1 vs 3.7 TB/s forward, 4.2 vs 3.9 TB/s input gradient).
+static int dw_mma_mode() {           // read per call: tests switch it with os.environ
+    const char* e = getenv("PB_DW_MMA");
+    return !e || !e[0] ? -1 : (e[0] == '0' ? 0 : 1);
+}
 static bool mma_class(const DwDims& d) {
-    return d.kT == 1 && d.kH == d.kW && (d.kH == 3 || d.kH == 5) && d.sH == 1 && d.sW == 1 && d.sT == 1 &&
-           d.pH == d.pW && d.pH == d.kH / 2 && d.C % 8 == 0 && d.Ho == d.H && d.Wo == d.W;
+    const bool shape_ok = d.kT == 1 && d.kH == d.kW && (d.kH == 3 || d.kH == 5) && d.sH == 1 && d.sW == 1 && d.sT == 1 &&
+                          d.pH == d.pW && d.pH == d.kH / 2 && d.C % 8 == 0 && d.Ho == d.H && d.Wo == d.W;
+    if (!shape_ok || dw_mma_mode() == 0) return false;
+    if (dw_mma_mode() == 1) return true;
+    return d.kH == 3 && d.W <= 14 && d.H >= 12 && d.C >= 400;
 }
 
 bool dw_fwd_mma(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y, const DwDims& d, cudaStream_t st) {
-    if (!dw_mma_enabled() || !mma_class(d)) return false;
+    if (!mma_class(d)) return false;
     if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0) return false;
     return d.kH == 3 ? launch_mma<3>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st)
                      : launch_mma<5>(x, w_tc, y, d.B, d.C, d.T, d.To, d.H, d.W, d.pT, 0, st);
@@ -446,7 +476,7 @@ bool dw_fwd_mma(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y, con
 
 // stride-1 input gradient == correlation of dy with the flipped filter: dx[t] reads dy[t + pT]
 bool dw_dgrad_mma(const __nv_bfloat16* dy, const float* w_tc, __nv_bfloat16* dx, const DwDims& d, cudaStream_t st) {
-    if (!dw_mma_enabled() || !mma_class(d)) return false;
+    if (!mma_class(d)) return false;
     if (((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) != 0) return false;
     return d.kH == 3 ? launch_mma<3>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st)
                      : launch_mma<5>(dy, w_tc, dx, d.B, d.C, d.To, d.T, d.H, d.W, -d.pT, 1, st);

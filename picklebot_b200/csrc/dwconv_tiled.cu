@@ -49,6 +49,8 @@ struct DwTile {
     long long ntiles;
     int stage_bytes, box_bytes, box2_bytes, stages;
     int flip;
+    int kT, padT;              // temporal taps (forward kernel only) and frames of padding before the first one
+    int src_T, sbuf_T;         // frames of the source tensor / of the stream buffer (0: not streaming)
 };
 
 __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
@@ -114,11 +116,11 @@ __device__ __forceinline__ void pipeline_init(TileCtx& cx, const DwTile& p) {
 
 // 5x5 filters: taps of this CTA's channel block as fp32 [tap][Cb] in shared memory (all threads, before the
 // role split); `flip` reverses the tap order (stride-1 input gradient).
-template <int K>
+template <int TAPS>
 __device__ __forceinline__ void stage_taps(float* wsm, const float* __restrict__ w_tc, const DwTile& p, int c_base, int flip) {
-    for (int e = threadIdx.x; e < K * K * p.Cb; e += DWT_THREADS) {
+    for (int e = threadIdx.x; e < TAPS * p.Cb; e += DWT_THREADS) {
         const int tap = e / p.Cb, c = e - tap * p.Cb;
-        const int src = flip ? K * K - 1 - tap : tap;
+        const int src = flip ? TAPS - 1 - tap : tap;
         wsm[e] = (c_base + c < p.C) ? w_tc[(long long)src * p.C + c_base + c] : 0.f;
     }
     __syncthreads();
@@ -169,7 +171,7 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
     pdl_trigger();
     pipeline_init(cx, p);
     pdl_wait();                 // barrier setup above overlaps the previous kernel's tail
-    if constexpr (K == 5) stage_taps<K>(reinterpret_cast<float*>(ring + (size_t)p.stages * p.stage_bytes), w_tc, p, c_base, p.flip);
+    if constexpr (K == 5) stage_taps<K * K>(reinterpret_cast<float*>(ring + (size_t)p.stages * p.stage_bytes), w_tc, p, c_base, p.flip);
     const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid >= DWT_CONSUMERS) {
@@ -287,6 +289,120 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// (kT,3,3) forward with temporal stride 1: MoviNetBottleneck.conv (movinet.py:52-61) and its causal streaming
+// form (CausalConv3d, movinet.py:23-39).  A stage holds the kT source frames of one destination tile, fetched
+// frame by frame: frame to - padT + kt of x, or -- streaming -- of the stream buffer when that index is negative
+// (the tail of the previous chunk, resident in HBM); frames outside both are zero-filled by the TMA unit, which
+// is the symmetric temporal padding of the non-causal layers.  All kT*9 taps sit in shared memory as fp32 [tap][Cb].
+// ------------------------------------------------------------------------------------------------
+template <int KT, int S, int WS>
+__global__ void __launch_bounds__(DWT_THREADS, 2)
+dw_fwd3d_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmS,
+                    const float* __restrict__ w_tc, __nv_bfloat16* __restrict__ y, const DwTile p) {
+    constexpr int K = 3;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ TileCtx cx;
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* ring = smem_raw + (((raw + 127u) & ~127u) - raw);
+    const int tid = threadIdx.x;
+    const int c_base = blockIdx.y * p.Cb;
+    const int cb_bytes = p.Cb * 2;
+    const int frame_bytes = (p.box_bytes + 127) / 128 * 128;
+    pdl_trigger();
+    pipeline_init(cx, p);
+    pdl_wait();
+    stage_taps<KT * K * K>(reinterpret_cast<float*>(ring + (size_t)p.stages * p.stage_bytes), w_tc, p, c_base, 0);
+    const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid >= DWT_CONSUMERS) {
+        if (tid == DWT_CONSUMERS) {
+            tma_prefetch_desc(&tmX);
+            if (p.sbuf_T > 0) tma_prefetch_desc(&tmS);
+            producer_loop(cx, p, ring, my_tiles, (uint32_t)(KT * p.box_bytes), [&](uint8_t* st, uint64_t* bar, const int4& c) {
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) {
+                    const int fi = c.y - p.padT + kt;                       // source frame of tap kt (c.y = destination frame)
+                    if (fi < 0 && p.sbuf_T > 0)
+                        tma_load_5d(st + kt * frame_bytes, &tmS, bar, c_base, c.w * S - p.pS, c.z * S - p.pS, p.sbuf_T + fi, c.x);
+                    else
+                        tma_load_5d(st + kt * frame_bytes, &tmX, bar, c_base, c.w * S - p.pS, c.z * S - p.pS, fi, c.x);
+                }
+            });
+        }
+        return;
+    }
+
+    const int ppp = DWT_CONSUMERS / p.Gb;
+    const int g = tid % p.Gb;
+    const bool active = tid < ppp * p.Gb && (c_base + g * 4) < p.C;
+    const int slot = tid / p.Gb;
+    const uint32_t wsm_g = smem_u32(ring + (size_t)p.stages * p.stage_bytes) + (uint32_t)(g * 16);
+    const int nstrips = p.Wt / WS;
+    const int items = p.Ht * nstrips;
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t row_bytes = (uint32_t)(p.Wi * cb_bytes);
+    const int lane = tid & 31;
+
+    for (long long n = 0; n < my_tiles; ++n) {
+        const int s = (int)(n % p.stages);
+        mbar_wait(&cx.full[s], (uint32_t)((n / p.stages) & 1));
+        const int4 c = cx.coord[s];
+        const uint32_t tile = ring_u32 + (uint32_t)(s * p.stage_bytes) + (uint32_t)(g * 8);
+        if (active) {
+            ItemIter it;
+            it.start(slot, ppp, nstrips);
+            for (int idx = slot; idx < items; idx += ppp, it.next()) {
+                const int ho = c.z + it.hl;
+                if (ho >= p.Ho) break;
+                float2 acc[WS][2];
+#pragma unroll
+                for (int o = 0; o < WS; ++o) { acc[o][0] = make_float2(0.f, 0.f); acc[o][1] = make_float2(0.f, 0.f); }
+#pragma unroll 1
+                for (int kt = 0; kt < KT; ++kt) {
+                    uint32_t rowa = tile + (uint32_t)(kt * frame_bytes) + (uint32_t)(it.hl * S) * row_bytes +
+                                    (uint32_t)(it.strip * WS * S * cb_bytes);
+#pragma unroll
+                    for (int i = 0; i < K; ++i, rowa += row_bytes) {
+                        constexpr int NJ = (WS - 1) * S + K;
+                        float2 win[NJ][2];
+                        uint32_t a = rowa;
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j, a += cb_bytes) {
+                            const uint2 u = lds64(a);
+                            win[j][0] = unpack2(u.x); win[j][1] = unpack2(u.y);
+                        }
+#pragma unroll
+                        for (int t = 0; t < K; ++t) {
+                            const float4 w4 = lds128f(wsm_g + (uint32_t)(((kt * K + i) * K + t) * p.Cb * 4));
+                            const float2 w0 = make_float2(w4.x, w4.y), w1 = make_float2(w4.z, w4.w);
+#pragma unroll
+                            for (int o = 0; o < WS; ++o) {
+                                ffma2(acc[o][0], win[o * S + t][0], w0);
+                                ffma2(acc[o][1], win[o * S + t][1], w1);
+                            }
+                        }
+                    }
+                }
+                const int wo0 = c.w + it.strip * WS;
+                __nv_bfloat16* yp = y + ((((long long)c.x * p.To + c.y) * p.Ho + ho) * p.Wo + wo0) * p.C + c_base + g * 4;
+#pragma unroll
+                for (int o = 0; o < WS; ++o) {
+                    if (wo0 + o < p.Wo) {
+                        uint2 out;
+                        out.x = pack_bf16x2(acc[o][0].x, acc[o][0].y);
+                        out.y = pack_bf16x2(acc[o][1].x, acc[o][1].y);
+                        *reinterpret_cast<uint2*>(yp) = out;
+                    }
+                    yp += p.C;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cx.empty[s]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // stride-2 input gradient: destination tile of dx [Ht][Wt] (Ht, Wt even, tile origin even), source halo of
 // dy rows h0/2 - P/2 .. , same for columns.
 //   dx[h][w] = sum_{i,j : (h+p-i), (w+p-j) even} dy[(h+p-i)/2][(w+p-j)/2] * w[i][j]
@@ -306,7 +422,7 @@ dw_dgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap tmD, const float* __r
     pdl_trigger();
     pipeline_init(cx, p);
     pdl_wait();                 // barrier setup above overlaps the previous kernel's tail
-    if constexpr (K == 5) stage_taps<K>(reinterpret_cast<float*>(ring + (size_t)p.stages * p.stage_bytes), w_tc, p, c_base, 0);
+    if constexpr (K == 5) stage_taps<K * K>(reinterpret_cast<float*>(ring + (size_t)p.stages * p.stage_bytes), w_tc, p, c_base, 0);
     const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (tid >= DWT_CONSUMERS) {
@@ -530,12 +646,13 @@ struct PlanIn {
     int pS;
     int with_dst_tile;     // wgrad: the dy tile is staged too
     int reserve;           // shared memory kept for other uses (5x5 taps), bytes
+    int frames = 1;        // source frames staged per tile (temporal taps of the (kT,3,3) kernels)
 };
 
 static bool plan_tile(const PlanIn& in, DwTile& p) {
     p.B = in.B; p.C = in.C; p.To = in.To; p.Ho = in.Ho; p.Wo = in.Wo;
     p.pS = in.pS;
-    p.nblk = ceil_div(in.C, 128);
+    p.nblk = ceil_div(in.C, in.frames > 1 ? 64 : 128);     // kT source frames per stage: narrower blocks, larger tiles
     p.Cb = (ceil_div(in.C, p.nblk) + 7) / 8 * 8;
     if (in.with_dst_tile && in.C > 128) {
         // weight gradient: a thread is (4 channels, filter row), so only multiples of Gb*K threads work; pick the
@@ -557,7 +674,7 @@ static bool plan_tile(const PlanIn& in, DwTile& p) {
     // destination pixels to staged source pixels (halo efficiency), then the larger tile.
     // per stage: 3 stages x 2 CTAs fit in one SM; the 5x5 kernels (issue-bound, wide halos) trade the third stage
     // for larger tiles, i.e. less halo re-fetch
-    const int budget = (in.K == 5 ? 46 : 34) * 1024;
+    const int budget = in.frames > 1 ? (104 * 1024 - in.reserve) / 2 : (in.K == 5 ? 46 : 34) * 1024;
     const int hstep = (S == 0) ? 2 : 1;
     double best_score = -1.0;
     int best_ht = 0, best_wt = 0;
@@ -566,7 +683,7 @@ static bool plan_tile(const PlanIn& in, DwTile& p) {
         int wi = src_extent(wt);
         if (wi > 256 || wt > 256) continue;
         for (int ht = hstep; ht <= in.Ho + hstep - 1; ht += hstep) {
-            long long bytes = (long long)src_extent(ht) * wi * p.Cb * 2 + (long long)in.with_dst_tile * ht * wt * p.Cb * 2;
+            long long bytes = (long long)in.frames * src_extent(ht) * wi * p.Cb * 2 + (long long)in.with_dst_tile * ht * wt * p.Cb * 2;
             if (bytes > budget || src_extent(ht) > 256) break;
             int th = ceil_div(in.Ho, ht);
             int ht_bal = ceil_div(in.Ho, th);
@@ -587,7 +704,7 @@ static bool plan_tile(const PlanIn& in, DwTile& p) {
     p.Ht = best_ht; p.tiles_h = ceil_div(in.Ho, best_ht); p.Hi = src_extent(best_ht);
     p.box_bytes = p.Hi * p.Wi * p.Cb * 2;
     p.box2_bytes = in.with_dst_tile ? p.Ht * p.Wt * p.Cb * 2 : 0;
-    p.stage_bytes = (p.box_bytes + 127) / 128 * 128 + (p.box2_bytes + 127) / 128 * 128;
+    p.stage_bytes = in.frames * ((p.box_bytes + 127) / 128 * 128) + (p.box2_bytes + 127) / 128 * 128;
     p.stages = std::min(DWT_MAX_STAGES, (108 * 1024 - in.reserve) / p.stage_bytes);
     if (p.stages < 2) return false;
     p.flip = 0;
@@ -697,6 +814,52 @@ static bool launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float*
     return true;
 }
 
+// (kT,3,3), temporal stride 1: x [B][T][H][W][C] (+ optional stream buffer [B][kT-1][H][W][C]) -> y [B][To][Ho][Wo][C]
+// with To = T + 2*pT - kT + 1 (non-causal) or To = T (streaming: padT = kT - 1 frames of history).
+template <int KT, int S, int WS>
+static bool launch_fwd3d(const __nv_bfloat16* x, const __nv_bfloat16* sbuf, const float* w_tc, __nv_bfloat16* y,
+                         const DwDims& d, int padT, cudaStream_t st) {
+    DwTile p;
+    constexpr int TAPS_BYTES = KT * 9 * 128 * 4;                            // fp32 [tap][Cb <= 128]
+    PlanIn in{d.B, d.C, d.To, d.Ho, d.Wo, 3, S, WS, d.pH, 0, TAPS_BYTES};
+    in.frames = KT;
+    if (!plan_tile(in, p)) return false;
+    p.nzf = 0; p.f_first = 0; p.f_step = 1; p.f_count = d.To; p.src_first = 0; p.src_step = 1;
+    p.ntiles = (long long)p.B * p.f_count * p.tiles_h * p.tiles_w;
+    p.kT = KT; p.padT = padT; p.src_T = d.T; p.sbuf_T = sbuf ? KT - 1 : 0;
+    p.flip = 0;
+    CUtensorMap tm, ts;
+    if (make_map5(&tm, x, d.C, d.W, d.H, d.T, d.B, p.Cb, p.Wi, p.Hi) != PB_OK) return false;
+    ts = tm;
+    if (sbuf && make_map5(&ts, sbuf, d.C, d.W, d.H, KT - 1, d.B, p.Cb, p.Wi, p.Hi) != PB_OK) return false;
+    static unsigned long long once = 0;
+    set_smem_once(dw_fwd3d_tma_kernel<KT, S, WS>, once);
+    (void)launch_pdl(dw_fwd3d_tma_kernel<KT, S, WS>, dim3(persistent_grid(p)), dim3(DWT_THREADS),
+                     (size_t)p.stages * p.stage_bytes + 128 + TAPS_BYTES, st, tm, ts, w_tc, y, p);
+    return true;
+}
+
+static bool movinet3d_class(const DwDims& d) {
+    return (d.kT == 3 || d.kT == 5) && d.kH == 3 && d.kW == 3 && d.sT == 1 && d.sH == d.sW && (d.sH == 1 || d.sH == 2) &&
+           d.pH == 1 && d.pW == 1 && d.C % 8 == 0;
+}
+
+template <int KT>
+static bool dispatch_fwd3d(const __nv_bfloat16* x, const __nv_bfloat16* sbuf, const float* w_tc, __nv_bfloat16* y,
+                           const DwDims& d, int padT, cudaStream_t st) {
+    const bool s7 = d.Wo % 7 == 0;
+    if (d.sH == 1) return s7 ? launch_fwd3d<KT, 1, 7>(x, sbuf, w_tc, y, d, padT, st) : launch_fwd3d<KT, 1, 4>(x, sbuf, w_tc, y, d, padT, st);
+    return s7 ? launch_fwd3d<KT, 2, 7>(x, sbuf, w_tc, y, d, padT, st) : launch_fwd3d<KT, 2, 4>(x, sbuf, w_tc, y, d, padT, st);
+}
+
+// causal streaming forward (pb_stream_dwconv3d_fwd): d.pT == kT - 1 frames of history from `sbuf`
+bool dw_stream_fwd_tiled(const __nv_bfloat16* x, const __nv_bfloat16* sbuf, const float* w_tc, __nv_bfloat16* y,
+                         const DwDims& d, cudaStream_t st) {
+    if (!movinet3d_class(d) || !sbuf) return false;
+    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(sbuf)) & 15) != 0) return false;
+    return d.kT == 3 ? dispatch_fwd3d<3>(x, sbuf, w_tc, y, d, 2, st) : dispatch_fwd3d<5>(x, sbuf, w_tc, y, d, 4, st);
+}
+
 static bool mobilenet_class(const DwDims& d) {
     return d.kT == 1 && d.kH == d.kW && (d.kH == 3 || d.kH == 5) && d.sH == d.sW && (d.sH == 1 || d.sH == 2) &&
            d.pH == d.pW && d.pH == d.kH / 2 && d.C % 8 == 0;
@@ -709,6 +872,8 @@ static bool strip7(int wo) { return wo % 7 == 0; }
 
 template <> bool dw_fwd_tiled<__nv_bfloat16>(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y,
                                             const DwDims& d, cudaStream_t st) {
+    if (movinet3d_class(d) && aligned16(x, y) && d.pT == d.kT / 2)      // MoViNet's symmetric temporal padding
+        return d.kT == 3 ? dispatch_fwd3d<3>(x, nullptr, w_tc, y, d, 1, st) : dispatch_fwd3d<5>(x, nullptr, w_tc, y, d, 2, st);
     if (!mobilenet_class(d) || !aligned16(x, y)) return false;
     if (dw_fwd_mma(x, w_tc, y, d, st)) return true;            // stride 1: tensor-core kernel (dwconv_mma.cu)
     if (d.kH == 3 && d.sH == 1)

@@ -48,9 +48,36 @@ rowscale_kernel(const T* x, const float* __restrict__ gate, const float* __restr
     store8(y + idx * 8, v);
 }
 
+// Cumulative mean for the streaming mode (MoViNet stream buffers, config 4): one block, so that every thread reads
+// the old row count before thread 0 advances it.
+__global__ void __launch_bounds__(1024)
+stream_pool_update_kernel(const float* __restrict__ chunk_mean, long long R, float* __restrict__ sum,
+                          long long* __restrict__ rows, float* __restrict__ mean_out, int n) {
+    pdl_trigger();
+    pdl_wait();
+    const long long seen = *rows + R;
+    __syncthreads();
+    const float inv = 1.0f / (float)seen, fr = (float)R;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float sacc = sum[i] + chunk_mean[i] * fr;
+        sum[i] = sacc;
+        mean_out[i] = sacc * inv;
+    }
+    if (threadIdx.x == 0) *rows = seen;
+}
+
 }  // namespace pb
 
 using namespace pb;
+
+extern "C" int pb_stream_pool_update(const float* chunk_mean, long long R, float* sum, long long* rows, float* mean_out,
+                                     int B, int C, pb_stream_t stream) {
+    PB_REQUIRE(chunk_mean && sum && rows && mean_out && B > 0 && C > 0 && R > 0, "stream_pool_update: bad args");
+    (void)launch_pdl(stream_pool_update_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, chunk_mean, R, sum, rows,
+                     mean_out, B * C);
+    PB_CHECK_LAUNCH("stream_pool_update_kernel");
+    return PB_OK;
+}
 
 extern "C" int pb_pool_fwd(const void* x, int dtype, int B, long long R, int C, float* mean, pb_stream_t stream) {
     PB_REQUIRE(x && mean && B > 0 && B <= 65535 && R > 0 && C > 0 && C % 8 == 0 && C <= 2048, "pool_fwd: bad args");

@@ -136,3 +136,52 @@ class GraphedForward:
             self.x.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.logits
+
+
+class GraphedStream:
+    """Causal streaming inference of ``MoViNetA2`` (``forward_stream``), one CUDA graph per chunk shape: the stream
+    state (tail frames of every temporal depthwise conv, cumulative squeeze-excite / head sums and counts) lives in
+    HBM and is only ever updated in place by the kernels, so ONE captured chunk step serves every chunk of every clip.
+
+        stream = GraphedStream(model.eval(), example_chunk)      # (B,3,Tc,H,W), e.g. the uint8 view of 8 frames
+        stream.reset()                                           # new clip: zero the state in place
+        for chunk in clip_chunks: logits = stream(chunk)         # logits after the frames seen so far (static tensor)
+    """
+
+    def __init__(self, model: torch.nn.Module, example_chunk: torch.Tensor,
+                 autocast_dtype: Optional[torch.dtype] = torch.bfloat16):
+        if model.training:
+            raise ValueError("GraphedStream captures an inference pass: call model.eval() first")
+        self.model, self.autocast_dtype = model, autocast_dtype
+        self.x = torch.empty_strided(example_chunk.shape, example_chunk.stride(), dtype=example_chunk.dtype,
+                                     device=example_chunk.device)
+        self.x.copy_(example_chunk)
+        self.state = model.init_stream_state()
+        side = torch.cuda.Stream(device=example_chunk.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):                       # allocates the state tensors and warms the weight caches
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        before = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.logits = self._eager()
+        self.launches = _lib.launch_count() - before
+        self.reset()
+
+    @torch.no_grad()
+    def _eager(self) -> torch.Tensor:
+        if self.autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                return self.model.forward_stream(self.x, self.state)[0]
+        return self.model.forward_stream(self.x, self.state)[0]
+
+    def reset(self) -> None:
+        self.model.reset_stream_state(self.state)
+
+    def __call__(self, chunk: torch.Tensor) -> torch.Tensor:
+        if chunk.data_ptr() != self.x.data_ptr():
+            self.x.copy_(chunk, non_blocking=True)
+        self.graph.replay()
+        return self.logits

@@ -105,8 +105,8 @@ class MoviNetBottleneck(nn.Module):
     # ----- streaming (inference only) ----------------------------------------------------------
     @torch.no_grad()
     def forward_stream(self, x5: torch.Tensor, state: dict) -> torch.Tensor:
-        """x5: NDHWC chunk.  ``state`` carries 'buf' (last kT-1 expanded frames), 'se_sum' [B][C] and
-        'frames' (count of pooled positions so far)."""
+        """x5: NDHWC chunk.  ``state`` carries 'buf' (last kT-1 expanded frames), 'se_sum' [B][C] and 'se_rows'
+        (pooled positions so far, device scalar); all of it is allocated on first use and updated in place."""
         cfg = self._cfg()
         if cfg.s[0] != 1:
             raise NotImplementedError("streaming needs temporal stride 1")
@@ -115,15 +115,19 @@ class MoviNetBottleneck(nn.Module):
         Cexp, Cout = self.expand.weight.shape[0], self.project.weight.shape[0]
         y1 = blocks.pw_fwd(x5.view(-1, Cin), self.expand.weight, self._cache, "w1").view(B, T, H, W, Cexp)
         w_tc = self._cache.get(("wdw", dt), self.conv.weight, lambda: ops.dw_weight_tapmajor(self.conv.weight, dt))
-        y2, state["buf"] = ops.stream_dwconv_fwd(y1, state.get("buf"), w_tc, cfg.k, cfg.s, cfg.p)
+        # stream state lives in HBM and is updated in place by the kernels (no host-side arithmetic, so a chunk
+        # step can be captured in a CUDA graph): 'buf' = last kT-1 expanded frames, 'se_sum'/'se_rows' = running sum
+        # and count behind the cumulative squeeze-excite mean
+        if cfg.k[0] > 1 and state.get("buf") is None:
+            state["buf"] = torch.zeros((B, cfg.k[0] - 1, H, W, Cexp), dtype=dt, device=x5.device)
+        y2, state["buf"] = ops.stream_dwconv_fwd(y1, state.get("buf"), w_tc, cfg.k, cfg.s, cfg.p, inplace=True)
         _, To, Ho, Wo, _ = y2.shape
         gate = None
         if self.squeeze_excite is not None:
-            n = To * Ho * Wo
-            chunk_sum = ops.pool_fwd(y2, B, Cexp) * float(n)
-            state["se_sum"] = chunk_sum if "se_sum" not in state else state["se_sum"] + chunk_sum
-            state["se_n"] = state.get("se_n", 0) + n
-            pooled = state["se_sum"] / float(state["se_n"])
+            if state.get("se_sum") is None:
+                state["se_sum"] = torch.zeros((B, Cexp), dtype=torch.float32, device=x5.device)
+                state["se_rows"] = torch.zeros((), dtype=torch.int64, device=x5.device)
+            pooled = ops.stream_pool_update(ops.pool_fwd(y2, B, Cexp), To * Ho * Wo, state["se_sum"], state["se_rows"])
             w1, b1, w2, b2 = self.squeeze_excite.params()
             _, gate = ops.se_fc_fwd(pooled, w1.reshape(w1.shape[0], -1), b1, w2.reshape(w2.shape[0], -1), b2)
         z = blocks.pw_fwd(y2.view(-1, Cexp), self.project.weight, self._cache, "w2", gate=gate,
@@ -222,7 +226,18 @@ class MoViNetA2(nn.Module):
 
     # ----- causal streaming inference (config 4) ------------------------------------------------
     def init_stream_state(self) -> dict:
-        return {"blocks": [dict() for _ in self._bottlenecks()], "head_sum": None, "head_n": 0}
+        """Empty stream state; the tensors (tail frames of every temporal conv, cumulative pooling sums and counts)
+        are allocated by the first ``forward_stream`` call and from then on only updated in place on the device."""
+        return {"blocks": [dict() for _ in self._bottlenecks()], "head_sum": None, "head_rows": None}
+
+    @staticmethod
+    def reset_stream_state(state: dict) -> dict:
+        """Start a new clip without re-allocating: zero every state tensor in place (graph-safe)."""
+        for st in state["blocks"] + [state]:
+            for v in st.values():
+                if isinstance(v, torch.Tensor):
+                    v.zero_()
+        return state
 
     @torch.no_grad()
     def forward_stream(self, chunk: torch.Tensor, state: dict) -> Tuple[torch.Tensor, dict]:
@@ -245,17 +260,16 @@ class MoViNetA2(nn.Module):
         eps0, mom0, rm0, rv0, _ = _bn_args(bn0)
         z = blocks.pw_fwd(x5.reshape(-1, Cin), self.conv[0].weight, self._cache, "tail_conv")
         a, _ = blocks.bn_forward(z, B, 640, bn0.weight, bn0.bias, rm0, rv0, None, False, eps0, mom0, hs, 0.0, None)
-        n = T * H * W
-        chunk_sum = ops.pool_fwd(a, B, 640) * float(n)
-        state["head_sum"] = chunk_sum if state["head_sum"] is None else state["head_sum"] + chunk_sum
-        state["head_n"] += n
-        feat = state["head_sum"] / float(state["head_n"])
+        if state["head_sum"] is None:
+            state["head_sum"] = torch.zeros((B, 640), dtype=torch.float32, device=chunk.device)
+            state["head_rows"] = torch.zeros((), dtype=torch.int64, device=chunk.device)
+        feat = ops.stream_pool_update(ops.pool_fwd(a, B, 640), T * H * W, state["head_sum"], state["head_rows"])
         fc1, fc2 = self.classifier[2], self.classifier[6]
-        u1 = ops.gemm_simt(feat, fc1.weight, 2048, 640, 640, 1, bias=fc1.bias)
+        u1 = ops.fc_fwd(feat, fc1.weight.detach(), fc1.bias.detach())
         _, _, rm1, rv1, _ = _bn_args(bn1)
         h1, _ = blocks.bn_forward(u1, B, 2048, bn1.weight, bn1.bias, rm1, rv1, None, False, float(bn1.eps), 0.1, hs,
                                   0.0, None)   # eval mode: the momentum argument is unused
-        logits = ops.gemm_simt(h1, fc2.weight, self.num_classes, 2048, 2048, 1, bias=fc2.bias)
+        logits = ops.fc_fwd(h1, fc2.weight.detach(), fc2.bias.detach())
         return logits, state
 
     def initialize_weights(self):

@@ -149,8 +149,8 @@ def dwconv_wgrad(x: torch.Tensor, dy: torch.Tensor, k, s, p) -> torch.Tensor:
     return dw_tc
 
 
-def stream_dwconv_fwd(x: torch.Tensor, sbuf: Optional[torch.Tensor], w_tc: torch.Tensor, k, s, p
-                      ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+def stream_dwconv_fwd(x: torch.Tensor, sbuf: Optional[torch.Tensor], w_tc: torch.Tensor, k, s, p,
+                      inplace: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Causal chunked depthwise conv; returns (y, new stream buffer)."""
     _chk(x, "stream_dwconv_fwd.x")
     B, T, H, W, C = x.shape
@@ -160,7 +160,8 @@ def stream_dwconv_fwd(x: torch.Tensor, sbuf: Optional[torch.Tensor], w_tc: torch
     if k[0] > 1:
         if sbuf is None:
             sbuf = torch.zeros((B, k[0] - 1, H, W, C), dtype=x.dtype, device=x.device)
-        new_buf = torch.empty_like(sbuf)
+        # in place when the chunk is at least as long as the history (the tail then comes from x alone)
+        new_buf = sbuf if (inplace and T >= k[0] - 1) else torch.empty_like(sbuf)
     call("pb_stream_dwconv3d_fwd", x.data_ptr(), _p(sbuf), w_tc.data_ptr(), y.data_ptr(), _p(new_buf), _dt(x),
          B, C, T, H, W, k[0], k[1], k[2], s[1], s[2], p[1], p[2], Ho, Wo, _st())
     return y, new_buf
@@ -261,6 +262,14 @@ def pool_fwd(x: torch.Tensor, B: int, C: int) -> torch.Tensor:
     R = x.numel() // (B * C)
     mean = torch.empty((B, C), dtype=torch.float32, device=x.device)
     call("pb_pool_fwd", x.data_ptr(), _dt(x), B, R, C, mean.data_ptr(), _st(), nbytes=x.numel() * x.element_size())
+    return mean
+
+
+def stream_pool_update(chunk_mean: torch.Tensor, R: int, ssum: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    """Cumulative mean over all chunks seen so far (in-place update of the stream state ``ssum`` / ``rows``)."""
+    B, C = chunk_mean.shape
+    mean = torch.empty_like(chunk_mean)
+    call("pb_stream_pool_update", chunk_mean.data_ptr(), R, ssum.data_ptr(), rows.data_ptr(), mean.data_ptr(), B, C, _st())
     return mean
 
 

@@ -58,6 +58,13 @@ DW_CASES = [
     (2, 136, 3, 9, 61, (1, 3, 3), (1, 1, 1), (1, 1, 1)),      # 61 columns: 3 windows padded to 4, ragged channel block
     (1, 64, 2, 5, 113, (1, 5, 5), (1, 1, 1), (2, 2, 2)),      # 113 columns: 5 windows padded to 8
     (5, 72, 3, 7, 7, (1, 5, 5), (1, 1, 1), (2, 2, 2)),        # 7x7 planes, odd frame count (two frames per tile)
+    # MoViNetA2's own (kT,3,3) layer shapes (movinet.py:99-136), 2 clips of 8 frames
+    (2, 64, 8, 56, 56, (3, 3, 3), (1, 1, 1), (1, 1, 1)),      # block2.2
+    (2, 96, 8, 56, 56, (3, 3, 3), (1, 2, 2), (1, 1, 1)),      # block3.0
+    (2, 240, 8, 28, 28, (5, 3, 3), (1, 2, 2), (2, 1, 1)),     # block4.0
+    (2, 240, 8, 14, 14, (5, 3, 3), (1, 1, 1), (2, 1, 1)),     # block5.0
+    (2, 480, 8, 14, 14, (5, 3, 3), (1, 2, 2), (2, 1, 1)),     # block6.0
+    (2, 480, 8, 7, 7, (3, 3, 3), (1, 1, 1), (1, 1, 1)),       # block6.5
 ]
 
 # (case index) -> must be served by the TMA fast paths in all three directions (every MobileNet class shape)
@@ -68,8 +75,15 @@ def _is_mobilenet_class(k, s, p):
 
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("case", DW_CASES)
-def test_dwconv_fwd_dgrad_wgrad(case, dt):
+@pytest.mark.parametrize("mma", ["default", "forced"])
+def test_dwconv_fwd_dgrad_wgrad(case, dt, mma, monkeypatch):
+    """mma = forced: PB_DW_MMA=1 sends every stride-1 (1,k,k) shape with >= 64 channels through the tensor-core
+    kernels of dwconv_mma.cu (by default only the shapes where they measured faster take that path)."""
     from picklebot_b200 import ops
+    if mma == "forced":
+        if dt != torch.bfloat16 or case[6] != (1, 1, 1) or case[5][0] != 1 or case[1] < 64:
+            pytest.skip("not a shape of the mma kernels")
+        monkeypatch.setenv("PB_DW_MMA", "1")
     B, C, T, H, W, k, s, p = case
     from picklebot_b200 import _lib
     x = rnd(B, T, H, W, C, dt=dt, seed=1)
@@ -91,9 +105,13 @@ def test_dwconv_fwd_dgrad_wgrad(case, dt):
     dw = ops.dw_weight_grad_from_tapmajor(dw_tc, w.shape)
     assert rel_err(dw, wr.grad) < (1e-4 if dt == torch.float32 else 2e-3)
     paths = _lib.path_counts()
+    movinet3d = k[0] in (3, 5) and k[1:] == (3, 3) and s[0] == 1 and s[1] == s[2] and p == (k[0] // 2, 1, 1)
     if dt == torch.bfloat16 and _is_mobilenet_class(k, s, p) and (s[0] == 1 or min(H, W) >= 2):
         # production path: no silent fall-through to the one-pixel-per-thread kernels
         assert paths["dw_fwd_tma"] == 1 and paths["dw_dgrad_tma"] == 1 and paths["dw_wgrad_tma"] == 1, paths
+    elif dt == torch.bfloat16 and movinet3d:
+        # MoviNetBottleneck.conv (kT,3,3): TMA-tiled forward; its gradients still run on the general-shape kernels
+        assert paths["dw_fwd_tma"] == 1 and paths["dw_dgrad_generic"] == 1 and paths["dw_wgrad_generic"] == 1, paths
     else:
         assert paths["dw_fwd_generic"] == 1 and paths["dw_dgrad_generic"] == 1 and paths["dw_wgrad_generic"] == 1, paths
 
@@ -116,8 +134,33 @@ def test_stream_dwconv_chunking_invariance(kt, dt):
         outs.append(y)
     y = torch.cat(outs, 1)
     assert rel_err(y.float(), yr) < tol(dt)
+    from picklebot_b200 import _lib
+    _lib.path_reset()
     whole, _ = ops.stream_dwconv_fwd(x, None, w_tc, k, s, p)
     assert torch.equal(whole, y)                      # chunking is bit-exact
+    paths = _lib.path_counts()
+    if dt == torch.bfloat16:                          # TMA-tiled: (1,3,3) stateless kernel, (kT,3,3) stream-buffer kernel
+        assert paths["dw_stream_tma"] == 1 and paths["dw_stream_generic"] == 0, paths
+
+
+@pytest.mark.parametrize("kt", [3, 5])
+def test_stream_dwconv_movinet_shapes(kt):
+    """The streaming kernel on MoViNetA2 layer shapes: an 8-frame chunk with a random (kT-1)-frame history."""
+    from picklebot_b200 import _lib, ops
+    for (C, H, W, s) in ((64, 56, 56, 1), (96, 56, 56, 2), (240, 14, 14, 1), (480, 14, 14, 2), (480, 7, 7, 1)):
+        B, T = 2, 8
+        k, st, p = (kt, 3, 3), (1, s, s), (0, 1, 1)
+        x = rnd(B, T, H, W, C, dt=torch.bfloat16, seed=4)
+        hist = rnd(B, kt - 1, H, W, C, dt=torch.bfloat16, seed=6)
+        w = rnd(C, 1, *k, seed=5, scale=0.5)
+        w_tc = ops.dw_weight_tapmajor(w, torch.bfloat16)
+        _lib.path_reset()
+        y, buf = ops.stream_dwconv_fwd(x, hist, w_tc, k, st, p)
+        assert _lib.path_counts()["dw_stream_tma"] == 1
+        xr = torch.cat([hist, x], 1).float().permute(0, 4, 1, 2, 3)
+        yr = F.conv3d(xr, w.to(torch.bfloat16).float(), None, st, p, 1, C).permute(0, 2, 3, 4, 1)
+        assert rel_err(y.float(), yr) < 1e-2, (C, H, W, s)
+        assert torch.equal(buf, torch.cat([hist, x], 1)[:, -(kt - 1):])
 
 
 GEMM_CASES = [(1, 300, 16, 16), (1, 1000, 24, 72), (3, 131, 72, 40), (2, 257, 960, 160), (1, 64, 960, 1280),

@@ -296,3 +296,41 @@ def test_movinet_stream_matches_stream_oracle():
     for i, (a, b) in enumerate(zip(outs, ref)):
         assert rel_err(a, b) < 2e-4, i
     assert torch.equal(outs[-1].argmax(1).cpu(), ref[-1].argmax(1))
+
+
+def test_movinet_stream_bf16_full_size_and_graph():
+    """Config 4 at its real size: 64 frames of 224x224 in 8-frame chunks, bf16 autocast, against the fp32 oracle of the
+    same streaming specification; the (kT,3,3) layers must run on the TMA-tiled stream kernel, and the captured
+    chunk graph (GraphedStream, state updated in place on the device) must reproduce the eager chunk loop."""
+    from picklebot_b200 import _lib
+    from picklebot_b200.graph import GraphedStream
+    g = golden("MoViNetA2")
+    m = build("MoViNetA2", g["num_classes"]).eval()
+    B, T, H, W, Tc = 2, 64, 224, 224, 8
+    clips = synth.synthetic_clips_u8(B, T, H, W).cuda()
+    x_u8 = clips.permute(0, 4, 1, 2, 3)                                  # (B,3,T,H,W) uint8 view
+    sd = O.clone_state(synthetic_checkpoint("MoViNetA2"), device="cuda")
+    xf = synth.clips_to_features(clips, torch.float32)
+    with torch.no_grad():
+        ref = O.movinet_a2_stream(sd, [xf[:, :, t0:t0 + Tc].contiguous() for t0 in range(0, T, Tc)])
+    _lib.path_reset()
+    state = m.init_stream_state()
+    outs = []
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        for t0 in range(0, T, Tc):
+            logits, state = m.forward_stream(x_u8[:, :, t0:t0 + Tc], state)
+            outs.append(logits.clone())
+    paths = _lib.path_counts()
+    assert paths["dw_stream_generic"] == 0 and paths["dw_stream_tma"] == 26 * (T // Tc), paths
+    assert paths["gemm_simt"] == 0 and paths["stem_simt"] == 0, paths
+    errs = [rel_err(a, b) for a, b in zip(outs, ref)]
+    print("\nMoViNetA2 stream bf16 vs fp32 oracle, per chunk:", " ".join(f"{e:.1e}" for e in errs))
+    _record({"test": "stream_bf16", "model": "MoViNetA2", "shape": [B, T, H, W], "per_chunk_logit_err": errs})
+    assert max(errs) < 3e-2
+    assert torch.equal(outs[-1].argmax(1).cpu(), ref[-1].argmax(1).cpu())
+    gs = GraphedStream(m, x_u8[:, :, :Tc])
+    for rep in range(2):                                               # two clips through the same graph and state
+        gs.reset()
+        for i, t0 in enumerate(range(0, T, Tc)):
+            lg = gs(x_u8[:, :, t0:t0 + Tc])
+            assert rel_err(lg, outs[i]) < 1e-2, (rep, i)
