@@ -60,7 +60,7 @@ CONFIGS = {
             metric=METRIC, scaling="strong",
             workload="MobileNetLarge3D training step, bf16 autocast, synthetic uint8 clips 3x16x224x224 "
                      "(BASELINE.json configs[2])"),
-    4: dict(model="MoViNetA2", mode="stream", clip=(64, 224, 224), chunk=8, micro=16, global_batch=16, nc=13,
+    4: dict(model="MoViNetA2", mode="stream", clip=(64, 224, 224), chunk=8, micro=32, global_batch=32, nc=13,
             metric="MoViNetA2 causal streaming inference clips/s (64-frame clips, 8-frame chunks)", scaling="weak",
             workload="MoViNetA2 causal streaming inference, bf16, 64-frame 224x224 uint8 clips fed as 8 chunks of 8 frames, "
                      "stream buffers and cumulative pooling state resident in HBM (BASELINE.json configs[3])"),
@@ -369,7 +369,8 @@ def main():
         else:
             from picklebot_b200 import dp as pbdp
             pbdp.broadcast_module(model)
-            buckets = pbdp.GradientBuckets(model.parameters(), grad_as_bucket_view=True)
+            # 1/world is folded into the loss scale below: the SUM all-reduce is the average, no division kernels
+            buckets = pbdp.GradientBuckets(model.parameters(), grad_as_bucket_view=True, average=False)
     opt = None
     if not train:
         pass
@@ -390,6 +391,8 @@ def main():
     # processes share the box's cores); gradients accumulate in place, the exchange runs after the last replay.
     gstep = gfwd = None
     gstream = None
+    # mean over the micro-batch / accumulation steps (/ ranks when GradientBuckets sums instead of averaging)
+    loss_scale = 1.0 / accum / (world if buckets is not None else 1)
     if mode == "stream" and not args.no_graphs:
         from picklebot_b200.graph import GraphedStream
         gstream = GraphedStream(model, clips[0][:, :cfg["chunk"]].permute(0, 4, 1, 2, 3))
@@ -401,7 +404,7 @@ def main():
         from picklebot_b200.graph import GraphedTrainStep
         with (buckets.no_sync() if buckets is not None else nullcontext()):
             gstep = GraphedTrainStep(model, clips[0].permute(0, 4, 1, 2, 3), labels[0],
-                                     loss_fn=lambda logits, y: pbloss.cross_entropy(logits, y, scale=1.0 / accum))
+                                     loss_fn=lambda logits, y: pbloss.cross_entropy(logits, y, scale=loss_scale))
         grad_list = [p.grad for p in model.parameters() if p.grad is not None]
 
     def zero_grads():
@@ -444,7 +447,7 @@ def main():
             return loss
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = net(x_u8.permute(0, 4, 1, 2, 3))        # (B,3,T,H,W) view of the uint8 NTHWC batch
-            loss = pbloss.cross_entropy(logits, y, scale=1.0 / accum)
+            loss = pbloss.cross_entropy(logits, y, scale=loss_scale)
         if world > 1 and not sync_grads:
             with (buckets.no_sync() if buckets is not None else net.no_sync()):
                 loss.backward()

@@ -59,7 +59,10 @@ class GradientBuckets:
     """
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group=None, bucket_cap_mb: float = 25.0,
-                 first_bucket_mb: float = 1.0, grad_as_bucket_view: bool = False):
+                 first_bucket_mb: float = 1.0, grad_as_bucket_view: bool = False, average: bool = True):
+        """``average=False``: the caller already folded 1/world into the loss scale, so the SUM all-reduce IS the
+        average and ``finish()`` launches no division kernels."""
+        self.average = average
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
@@ -180,7 +183,7 @@ class GradientBuckets:
             if w is not None and w != "local":
                 w.wait()
             flat = self._flat[i]
-            if self.world > 1:
+            if self.world > 1 and self.average:
                 flat.div_(self.world)
             if not self.grad_as_bucket_view:
                 off = 0

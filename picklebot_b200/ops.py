@@ -162,8 +162,10 @@ def stream_dwconv_fwd(x: torch.Tensor, sbuf: Optional[torch.Tensor], w_tc: torch
             sbuf = torch.zeros((B, k[0] - 1, H, W, C), dtype=x.dtype, device=x.device)
         # in place when the chunk is at least as long as the history (the tail then comes from x alone)
         new_buf = sbuf if (inplace and T >= k[0] - 1) else torch.empty_like(sbuf)
+    hist = 0 if sbuf is None else sbuf.numel()
     call("pb_stream_dwconv3d_fwd", x.data_ptr(), _p(sbuf), w_tc.data_ptr(), y.data_ptr(), _p(new_buf), _dt(x),
-         B, C, T, H, W, k[0], k[1], k[2], s[1], s[2], p[1], p[2], Ho, Wo, _st())
+         B, C, T, H, W, k[0], k[1], k[2], s[1], s[2], p[1], p[2], Ho, Wo, _st(),
+         nbytes=(x.numel() + y.numel() + 2 * hist) * x.element_size())   # chunk in, out, history read + rewritten
     return y, new_buf
 
 
