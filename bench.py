@@ -104,6 +104,19 @@ def parse():
     return args
 
 
+def measure_write_only_gbs(dev):
+    """HBM write-only bandwidth (a 1 GiB fill, best of 5): on B200 it is ~3.9 TB/s against ~6.5 TB/s for a copy, which
+    is the ceiling of the write-dominated kernels (the 1x1x1 expand GEMMs write 3-6x what they read)."""
+    buf = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    best = None
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); buf.zero_(); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return buf.numel() / best / 1e6
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -593,12 +606,26 @@ def main():
                     "frac": kt["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_kind + " copy bandwidth",
                     "share_of_step": kt["share"], "avg_launch_us": kt["avg_us"],
                     "alg_bytes_per_launch": kt["alg_bytes_per_launch"]}
+        roofline["hbm_write_only_GBps"] = measure_write_only_gbs(dev)
+        roofline["note"] = ("frac is against the copy bandwidth of MEASURED_PEAKS.json; a write-only stream reaches "
+                            "hbm_write_only_GBps on this GPU (measured here), the ceiling of write-dominated launches")
         dw = {k: v for k, v in kernels.items() if k.startswith("pb_dwconv3d")}
         if dw:
             b = sum(v["GBps"] * v["ms_per_step"] for v in dw.values())
             t = sum(v["ms_per_step"] for v in dw.values())
             roofline["depthwise_conv3d_GBps"] = b / t
             roofline["depthwise_conv3d_frac"] = b / t / peak
+
+    # Evidence capture: under `ncu --profile-from-start off` (tools/collect_evidence.sh) exactly one eager micro-batch
+    # (forward + loss + backward, every launch of the hot path once) runs between cudaProfilerStart/Stop.
+    if os.environ.get("PB_NCU_RANGE") and rank == 0:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        micro_step(clips[0], labels[0], True, eager=True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if train:
+            zero_grads()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
