@@ -80,8 +80,12 @@ def parse():
     ap.add_argument("--torch-mode", default="eager", choices=["eager", "compiled"],
                     help="--impl torch-b200 only: the reference's torch ops eagerly or under torch.compile")
     ap.add_argument("--no-torch-b200", action="store_true", help="skip the torch/cuDNN-on-this-B200 legs")
-    ap.add_argument("--torch-compile-budget", type=float, default=300.0,
-                    help="seconds the torch.compile(max-autotune-no-cudagraphs) leg may take before it is abandoned")
+    ap.add_argument("--torch-compile-budget", type=float, default=240.0,
+                    help="seconds the torch.compile leg may take before it is abandoned (0 disables it)")
+    ap.add_argument("--torch-compile-mode", default="default",
+                    help="torch.compile mode of the compiled leg.  The reference uses max-autotune-no-cudagraphs "
+                         "(train.py:181), whose autotuning takes ~630 s on the bench box: measured once per round "
+                         "(profiles/), while the default run uses mode='default' so that bench.py ends within minutes")
     ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS),
                     help="BASELINE.json configuration (1-based); 3 = the headline MobileNetLarge3D training step")
     ap.add_argument("--micro", type=int, default=None)
@@ -266,7 +270,7 @@ def run_torch_b200(args):
     labels = [synth.synthetic_labels(micro, cfg["nc"], seed=77 + a).to(dev) for a in range(2)]
     fwd = O.MODELS[cfg["model"]]
     if args.torch_mode == "compiled":
-        fwd = torch.compile(fwd, mode="max-autotune-no-cudagraphs")
+        fwd = torch.compile(fwd, mode=args.torch_compile_mode)
 
     def step():
         for a in range(accum):
@@ -295,7 +299,8 @@ def run_torch_b200(args):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    print(json.dumps({"mode": args.torch_mode, "value": args.global_batch / (ms / 1000.0), "unit": "clips/s",
+    print(json.dumps({"mode": args.torch_mode + (f" ({args.torch_compile_mode})" if args.torch_mode == "compiled" else ""),
+                      "value": args.global_batch / (ms / 1000.0), "unit": "clips/s",
                       "ms_per_step": ms, "steps": steps, "micro_batch": micro, "warmup_and_setup_s": warm_s,
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9, "torch": torch.__version__,
                       "cudnn": torch.backends.cudnn.version()}), flush=True)
@@ -311,7 +316,7 @@ def torch_b200_legs(args, local):
             continue
         cmd = [sys.executable, os.path.abspath(__file__), "--impl", "torch-b200", "--torch-mode", mode, "--steps",
                str(args.steps), "--micro", str(args.micro), "--global-batch", str(args.global_batch),
-               "--config", str(args.config)]
+               "--config", str(args.config), "--torch-compile-mode", args.torch_compile_mode]
         env = dict(os.environ, LOCAL_RANK=str(local))
         for k in ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
             env.pop(k, None)
@@ -328,7 +333,8 @@ def torch_b200_legs(args, local):
         out[mode]["wall_s"] = time.perf_counter() - t0
     out["what"] = ("the reference's torch ops (ATen/cuDNN) on this same B200: uint8 clips -> .to(bf16)/255 -> autocast(bf16) "
                    "forward + CE + backward at micro-batch 64, fused AdamW per 512 clips; eager with cudnn.benchmark "
-                   "(train.py:193,264-269) and torch.compile(mode='max-autotune-no-cudagraphs') (train.py:181)")
+                   f"(train.py:193,264-269) and torch.compile(mode='{args.torch_compile_mode}') (train.py:181 uses "
+                   "max-autotune-no-cudagraphs: ~630 s of autotuning here, measured once per round, see profiles/)")
     return out
 
 
@@ -585,11 +591,16 @@ def main():
                     gb = v["bytes"] / (v["ms"] * 1e6) if v["ms"] > 0 else 0
                     f.write(f"{v['ms']:9.3f} ms  {v['launches']:4d}x  {gb:8.1f} GB/s  {k}\n")
         tot_ms = sum(v["ms"] for v in summ.values())
+        write_peak = measure_write_only_gbs(dev)
         for name, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"]):
             gbs = v["bytes"] / (v["ms"] * 1e6) if v["ms"] > 0 else 0.0
+            # read/write-aware bound per launch: all bytes at the copy rate, or the written bytes at the write-only rate
+            bound_ms = sum(max(nb / (peak * 1e6), wb / (write_peak * 1e6)) for nb, wb in v["per_launch"])
             kernels[name] = {"launches_per_step": v["launches"] // max(1, args.profile_steps),
                              "ms_per_step": v["ms"] / max(1, args.profile_steps), "share": v["ms"] / tot_ms,
                              "GBps": gbs, "frac_of_hbm_peak": gbs / peak,
+                             "frac_of_rw_bound": bound_ms / v["ms"] if v["ms"] > 0 else 0.0,
+                             "written_share_of_bytes": v["wbytes"] / v["bytes"] if v["bytes"] else 0.0,
                              "avg_us": 1000.0 * v["ms"] / v["launches"],
                              "alg_bytes_per_launch": v["bytes"] / v["launches"]}
         top = next(iter(kernels))
@@ -606,9 +617,11 @@ def main():
                     "frac": kt["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_kind + " copy bandwidth",
                     "share_of_step": kt["share"], "avg_launch_us": kt["avg_us"],
                     "alg_bytes_per_launch": kt["alg_bytes_per_launch"]}
-        roofline["hbm_write_only_GBps"] = measure_write_only_gbs(dev)
-        roofline["note"] = ("frac is against the copy bandwidth of MEASURED_PEAKS.json; a write-only stream reaches "
-                            "hbm_write_only_GBps on this GPU (measured here), the ceiling of write-dominated launches")
+        roofline["hbm_write_only_GBps"] = write_peak
+        roofline["frac_of_rw_bound"] = kt["frac_of_rw_bound"]
+        roofline["note"] = ("frac is against the copy bandwidth of MEASURED_PEAKS.json.  A write-only stream reaches "
+                            "hbm_write_only_GBps on this GPU (measured here); frac_of_rw_bound uses, per launch, the "
+                            "larger of (all bytes / copy rate) and (written bytes / write-only rate)")
         dw = {k: v for k, v in kernels.items() if k.startswith("pb_dwconv3d")}
         if dw:
             b = sum(v["GBps"] * v["ms_per_step"] for v in dw.values())

@@ -106,24 +106,27 @@ class KernelProfiler:
     live roofline numbers; off (None) by default so the hot path pays nothing."""
 
     def __init__(self):
-        self.records = []          # (name, start_event, end_event, algorithmic_bytes, tag)
+        self.records = []          # (name, start_event, end_event, algorithmic_bytes, tag, written_bytes)
 
     def summary(self, by_tag: bool = False):
         import torch
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, nbytes, tag in self.records:
-            d = out.setdefault(name if not by_tag else f"{name}|{tag}", {"launches": 0, "ms": 0.0, "bytes": 0})
+        for name, e0, e1, nbytes, tag, wbytes in self.records:
+            d = out.setdefault(name if not by_tag else f"{name}|{tag}",
+                               {"launches": 0, "ms": 0.0, "bytes": 0, "wbytes": 0, "per_launch": []})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
             d["bytes"] += nbytes
+            d["wbytes"] += wbytes
+            d["per_launch"].append((nbytes, wbytes))
         return out
 
 
 PROFILER = None
 
 
-def call(name: str, *args, nbytes: int = 0, tag: str = "") -> None:
+def call(name: str, *args, nbytes: int = 0, tag: str = "", wbytes: int = 0) -> None:
     prof = PROFILER
     if prof is not None:
         import torch
@@ -136,7 +139,7 @@ def call(name: str, *args, nbytes: int = 0, tag: str = "") -> None:
         raise PicklebotKernelError(f"{name} failed (code {rc}): {msg.decode() if msg else '?'}")
     if prof is not None:
         e1.record()
-        prof.records.append((name, e0, e1, nbytes, tag))
+        prof.records.append((name, e0, e1, nbytes, tag, wbytes))
 
 
 def launch_count() -> int:

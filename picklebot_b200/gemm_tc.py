@@ -27,7 +27,7 @@ def gemm(A: torch.Tensor, Wb: torch.Tensor, N: int, K: int, Bw: int = 1, Bt: int
     C = torch.empty((rows, N), dtype=torch.bfloat16, device=A.device)
     sums = torch.empty((_lib.STAT_REPLICAS, 2, stat_mod), dtype=torch.float64, device=A.device) if stat_mod else None
     call("pb_pw_gemm_tc", A.data_ptr(), Wb.data_ptr(), Bw, _p(bias), _p(colscale), _p(coladd), C.data_ptr(),
-         _p(sums), stat_mod, Bt, R, K, N, _st(), nbytes=(A.numel() + C.numel() + Wb.numel()) * 2)
+         _p(sums), stat_mod, Bt, R, K, N, _st(), nbytes=(A.numel() + C.numel() + Wb.numel()) * 2, wbytes=C.numel() * 2)
     return (C, sums) if stat_mod else C
 
 

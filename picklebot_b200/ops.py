@@ -16,10 +16,12 @@ from ._lib import (ACT_HSIGMOID, ACT_HSWISH, ACT_LRELU, ACT_NONE, ACT_RELU, PB_B
                    PB_U8, STAT_REPLICAS)
 
 
-def call(name, *args, nbytes=0, tag=""):
+def call(name, *args, nbytes=0, tag="", wbytes=0):
+    """nbytes: algorithmic bytes of the launch (read + written), wbytes: the written part (a write-only stream tops
+    out at ~3.9 TB/s on B200 against ~6.5 TB/s for a copy, so the split matters for the roofline bound)."""
     if _lib.PROFILER is not None and not tag:
         tag = ",".join(str(a) for a in args if isinstance(a, int) and not isinstance(a, bool) and 0 < a < 100000)
-    _lib.call(name, *args, nbytes=nbytes, tag=tag)
+    _lib.call(name, *args, nbytes=nbytes, tag=tag, wbytes=wbytes)
 
 ACT_CODES = {"none": ACT_NONE, "relu": ACT_RELU, "hswish": ACT_HSWISH, "lrelu": ACT_LRELU,
              "hsigmoid": ACT_HSIGMOID}
@@ -126,7 +128,8 @@ def dwconv_fwd(x: torch.Tensor, w_tc: torch.Tensor, k, s, p) -> torch.Tensor:
     d = _dw_dims(x.shape, k, s, p)
     y = torch.empty((d[0], d[14], d[15], d[16], d[1]), dtype=x.dtype, device=x.device)
     call("pb_dwconv3d_fwd", x.data_ptr(), w_tc.data_ptr(), y.data_ptr(), _dt(x), *d, _st(),
-         nbytes=(x.numel() + y.numel()) * x.element_size() + w_tc.numel() * x.element_size())
+         nbytes=(x.numel() + y.numel()) * x.element_size() + w_tc.numel() * x.element_size(),
+         wbytes=y.numel() * y.element_size())
     return y
 
 
@@ -135,7 +138,8 @@ def dwconv_dgrad(dy: torch.Tensor, w_tc: torch.Tensor, x_shape, k, s, p) -> torc
     d = _dw_dims(x_shape, k, s, p)
     dx = torch.empty(tuple(x_shape), dtype=dy.dtype, device=dy.device)
     call("pb_dwconv3d_dgrad", dy.data_ptr(), w_tc.data_ptr(), dx.data_ptr(), _dt(dy), *d, _st(),
-         nbytes=(dx.numel() + dy.numel()) * dy.element_size() + w_tc.numel() * dy.element_size())
+         nbytes=(dx.numel() + dy.numel()) * dy.element_size() + w_tc.numel() * dy.element_size(),
+         wbytes=dx.numel() * dx.element_size())
     return dx
 
 
@@ -188,7 +192,7 @@ def gemm_simt(A: torch.Tensor, W: torch.Tensor, N: int, K: int, w_sn: int, w_sk:
     C = torch.empty((rows, N), dtype=A.dtype, device=A.device)
     call("pb_pw_gemm_simt", A.data_ptr(), W.data_ptr(), w_sn, w_sk, _p(bias), _p(ascale), _p(colscale),
          _p(coladd), C.data_ptr(), _dt(A), Bt, R, K, N, _st(),
-         nbytes=(A.numel() + C.numel() + N * K) * A.element_size())
+         nbytes=(A.numel() + C.numel() + N * K) * A.element_size(), wbytes=C.numel() * C.element_size())
     return C
 
 
@@ -231,7 +235,7 @@ def bn_act_fwd(z: torch.Tensor, scale, shift, mask, B: int, C: int, act: int, sl
     R = z.numel() // (B * C)
     out = torch.empty_like(z)
     call("pb_bn_act_fwd", z.data_ptr(), scale.data_ptr(), shift.data_ptr(), _p(mask), out.data_ptr(), _dt(z),
-         B, R, C, act, slope, _st(), nbytes=2 * z.numel() * z.element_size())
+         B, R, C, act, slope, _st(), nbytes=2 * z.numel() * z.element_size(), wbytes=z.numel() * z.element_size())
     return out
 
 
@@ -252,7 +256,8 @@ def bn_act_bwd(dout: torch.Tensor, dout_bcast: bool, z: torch.Tensor, scale, shi
     dz = torch.empty_like(z)
     call("pb_bn_act_bwd_apply", dout.data_ptr(), int(dout_bcast), z.data_ptr(), scale.data_ptr(), shift.data_ptr(),
          mean.data_ptr(), invstd.data_ptr(), _p(mask), small[2].data_ptr(), dz.data_ptr(), _dt(z), B, R, C, act,
-         slope, _st(), nbytes=(2 * z.numel() + (0 if dout_bcast else dout.numel())) * z.element_size())
+         slope, _st(), nbytes=(2 * z.numel() + (0 if dout_bcast else dout.numel())) * z.element_size(),
+         wbytes=z.numel() * z.element_size())
     return dz, small[0], small[1]
 
 

@@ -6,7 +6,7 @@ timeout 300 python __graft_entry__.py --smoke > gpurun_out/r02_smoke.txt 2>&1; t
 python tools/bw_probe.py > gpurun_out/r02_bw_probe.txt 2>&1
 timeout 300 python tools/dw_bench.py > gpurun_out/r02_dw_microbench.txt 2>&1
 PB_DW_MMA=1 timeout 300 python tools/dw_bench.py > gpurun_out/r02_dw_microbench_mma_forced.txt 2>&1
-PB_BENCH_DETAIL=gpurun_out/r02_kernel_detail_per_layer.txt timeout 1500 python bench.py --steps 4 --warmup 3 --torch-compile-budget ${COMPILE_BUDGET:-0} > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err
+PB_BENCH_DETAIL=gpurun_out/r02_kernel_detail_per_layer.txt timeout 1500 python bench.py --steps 4 --warmup 3 --torch-compile-budget ${COMPILE_BUDGET:-240} > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2>/dev/null
 for c in 2 4 5; do timeout 900 python bench.py --config $c --steps 3 --warmup 3 --torch-compile-budget 0 > gpurun_out/r02_bench_config$c.json 2> gpurun_out/r02_bench_config$c.err; done
 timeout 600 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-torch-b200 > gpurun_out/plain_range.log 2>&1 && \
