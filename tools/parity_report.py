@@ -50,8 +50,16 @@ for r in rows("model_bf16_parity.jsonl"):
     if r["test"] == "microbatch64":
         print(f"| micro-batch | {r['model']} | {'x'.join(map(str, r['shape']))} | {r['logits_ours_vs_fp32']:.1e} / {r['logits_torch_vs_fp32']:.1e} | "
               f"{r['grads_ours_vs_fp32']:.1e} / {r['grads_torch_vs_fp32']:.1e} | {r['logits_ours_vs_torch']:.1e}, {r['grads_ours_vs_torch']:.1e} |")
-    else:
+    elif r["test"] == "train_step_bf16":
         print(f"| train step | {r['model']} | {'x'.join(map(str, r['shape']))} | {r['logits_ours']:.1e} / {r['logits_torch_autocast']:.1e} | "
               f"{r['grads_ours']:.1e} / {r['grads_torch_autocast']:.1e} | {r['logits_ours_vs_torch']:.1e}, {r['grads_ours_vs_torch']:.1e} |")
+for r in rows("model_bf16_parity.jsonl"):
+    if r["test"] == "stream_bf16":
+        print(f"\nMoViNetA2 causal stream, {'x'.join(map(str, r['shape']))} in 8-frame chunks, per-chunk logits vs the fp32 oracle "
+              "stream (the synthetic checkpoint is chaotic along time; both bf16 paths drift alike):\n")
+        print("| chunk | " + " | ".join(str(i) for i in range(len(r["per_chunk_logit_err"]))) + " |")
+        print("|---|" + "---|" * len(r["per_chunk_logit_err"]))
+        print("| ours | " + " | ".join(f"{e:.1e}" for e in r["per_chunk_logit_err"]) + " |")
+        print("| torch autocast | " + " | ".join(f"{e:.1e}" for e in r["per_chunk_logit_err_torch_autocast"]) + " |")
 print("\nfp32 storage (the 1e-4 bar): eval logits vs the reference's golden fixtures <= 1e-4, train-step logits <= 1e-4, "
       "all-parameter gradient vector <= 1e-4 / 2e-4 / 5e-4 (Large / Small / MoViNetA2): tests/test_models_gpu.py.")

@@ -8,8 +8,8 @@ import sys
 
 # kernel function name fragment -> C-ABI entry point whose launches it serves
 FAMILIES = [("gemm_tc_kernel", "pb_pw_gemm_tc"), ("wgrad_tc_kernel", "pb_pw_wgrad_tc"),
-            ("dw_fwd_tma_kernel", "pb_dwconv3d_fwd"), ("dw_s1_mma_kernel", "pb_dwconv3d_fwd/dgrad (mma)"),
-            ("dw_fwd3d_tma_kernel", "pb_dwconv3d_fwd (kT,3,3)"), ("dw_dgrad_s2_tma_kernel", "pb_dwconv3d_dgrad"),
+            ("dw_fwd_tma_kernel", "pb_dwconv3d_fwd + stride-1 pb_dwconv3d_dgrad"), ("dw_s1_mma_kernel", "pb_dwconv3d_fwd/dgrad (mma)"),
+            ("dw_fwd3d_tma_kernel", "pb_dwconv3d_fwd (kT,3,3)"), ("dw_dgrad_s2_tma_kernel", "pb_dwconv3d_dgrad (stride 2)"),
             ("dw_wgrad_tma_kernel", "pb_dwconv3d_wgrad"), ("bn_act_fwd_kernel", "pb_bn_act_fwd"),
             ("bn_bwd_reduce_kernel", "pb_bn_act_bwd_reduce"), ("bn_bwd_apply_kernel", "pb_bn_act_bwd_apply"),
             ("stem_tc_fwd_kernel", "pb_stem_conv_fwd"), ("stem_tc_wgrad_kernel", "pb_stem_conv_wgrad"),
