@@ -450,7 +450,7 @@ def main():
                 logits, state = model.forward_stream(x_u8[:, t0:t0 + cfg["chunk"]].permute(0, 4, 1, 2, 3), state)
         return logits
 
-    def micro_step(x_u8, y, sync_grads, eager=False):
+    def micro_step(x_u8, y, sync_grads, eager=False, first=True):
         if mode == "stream":
             return stream_clip(x_u8, eager)
         if mode == "infer":
@@ -459,7 +459,9 @@ def main():
             with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
                 return model(x_u8.permute(0, 4, 1, 2, 3))
         if gstep is not None and not eager:
-            loss = gstep(x_u8.permute(0, 4, 1, 2, 3), y)
+            # the optimizer moved the weights before the first micro-batch of a step only: the others replay the
+            # graph that skips the weight casts
+            loss = gstep(x_u8.permute(0, 4, 1, 2, 3), y, weights_changed=first)
             if sync_grads and buckets is not None:
                 buckets.reduce_all()
                 buckets.finish()
@@ -479,7 +481,7 @@ def main():
     def step_resident(eager=False):
         tot = None
         for a in range(accum):
-            l = micro_step(clips[a], labels[a], a == accum - 1, eager)
+            l = micro_step(clips[a], labels[a], a == accum - 1, eager, first=a == 0)
             tot = l if (tot is None or not train) else tot + l
         if train:
             opt.step()
@@ -514,8 +516,10 @@ def main():
     n0 = _lib.launch_count()
     ms = timed(step_resident, args.steps)
     launches = _lib.launch_count() - n0
-    if gstep is not None or gfwd is not None:   # replays launch the captured kernels without passing the C ABI
-        launches += args.steps * accum * (gstep or gfwd).launches
+    if gstep is not None:                       # replays launch the captured kernels without passing the C ABI
+        launches += args.steps * (gstep.launches + (accum - 1) * gstep.launches_warm)
+    if gfwd is not None:
+        launches += args.steps * accum * gfwd.launches
     if gstream is not None:
         launches += args.steps * accum * (clip_shape[0] // cfg["chunk"]) * gstream.launches
     clocks = sampler.stop() if rank == 0 else None
@@ -552,7 +556,7 @@ def main():
                 slot = seq[0] & 1
                 upload((a + 1) % accum, slot ^ 1)      # prefetch the next micro-batch (possibly the next step's first)
                 cur.wait_event(ready[slot])
-                l = micro_step(dbuf[slot], lbuf[slot], a == accum - 1)
+                l = micro_step(dbuf[slot], lbuf[slot], a == accum - 1, first=a == 0)
                 consumed[slot].record(cur)
                 tot = l if (tot is None or not train) else tot + l
                 seq[0] += 1
