@@ -45,7 +45,8 @@ int         pb_device_check(void);      /* PB_OK iff the current device is sm_10
 enum { PB_PATH_DW_FWD_TMA = 0, PB_PATH_DW_FWD_GENERIC, PB_PATH_DW_DGRAD_TMA, PB_PATH_DW_DGRAD_GENERIC,
        PB_PATH_DW_WGRAD_TMA, PB_PATH_DW_WGRAD_GENERIC, PB_PATH_GEMM_TC, PB_PATH_GEMM_SIMT,
        PB_PATH_WGRAD_TC, PB_PATH_WGRAD_SIMT, PB_PATH_STEM_TC, PB_PATH_STEM_SIMT,
-       PB_PATH_DW_BWD_FUSED_TMA, PB_PATH_DW_STREAM_TMA, PB_PATH_DW_STREAM_GENERIC, PB_PATH_COUNT };
+       PB_PATH_DW_BWD_FUSED_TMA, PB_PATH_DW_STREAM_TMA, PB_PATH_DW_STREAM_GENERIC,
+       PB_PATH_STEM_TMA /* subset of STEM_TC: uint8 clip staged by TMA */, PB_PATH_COUNT };
 long long   pb_path_count(int path);    /* calls served by `path` since load / the last reset; -1 if out of range */
 void        pb_path_reset(void);
 
@@ -124,6 +125,9 @@ int pb_cast_matrix(const float* src, void* dst, int dst_dtype, int rows, int col
                    pb_stream_t stream);
 /* dst[b][n][k] = bf16( W[n][k] * gate[b][k] )  -- squeeze-excite gate folded into pointwise_conv2. */
 int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, int Bt, int N, int K, pb_stream_t stream);
+/* transposed twin for the input gradient  dy2 = (dz W) * gate  of the same block (blocks.py se_pw2_backward):
+ * dst[b][k][n] = bf16(W[n][k] * gate[b][k]), W fp32 [N][K], gate fp32 [Bt][K], dst bf16 [Bt][K][N], N % 8 == 0. */
+int pb_fold_gate_t_bf16(const float* W, const float* gate, void* dst, int Bt, int N, int K, pb_stream_t stream);
 /* dst bf16 [F*N][F*K] = diag(W, ..., W) for W bf16 [N][K]: the weight of a row-folded GEMM.  A layer with
  * K <= 32 input channels is run as X'[rows/F][F*K] x dst^T = C'[rows/F][F*N], which is C[rows][N] in memory,
  * so that TMA moves 128-byte rows instead of 32-byte ones. */

@@ -32,6 +32,7 @@ SIGNATURES = {
     "pb_pw_wgrad_tc": "pppppppiliip",
     "pb_cast_matrix": "ppiiiip",
     "pb_fold_gate_bf16": "pppiiip",
+    "pb_fold_gate_t_bf16": "pppiiip",
     "pb_block_diag_bf16": "ppiiip",
     "pb_colstats": "pilipp",
     "pb_bn_finalize": "plppppiffpppppip",
@@ -58,7 +59,7 @@ PLAIN = ("pb_abi_version", "pb_last_error_string", "pb_launch_count", "pb_device
 # PB_PATH_* of include/picklebot_b200.h, in enum order
 PATHS = ("dw_fwd_tma", "dw_fwd_generic", "dw_dgrad_tma", "dw_dgrad_generic", "dw_wgrad_tma", "dw_wgrad_generic",
          "gemm_tc", "gemm_simt", "wgrad_tc", "wgrad_simt", "stem_tc", "stem_simt", "dw_bwd_fused_tma",
-         "dw_stream_tma", "dw_stream_generic")
+         "dw_stream_tma", "dw_stream_generic", "stem_tma")
 EXPORTS = tuple(SIGNATURES) + PLAIN
 
 

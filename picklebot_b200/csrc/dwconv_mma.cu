@@ -75,24 +75,6 @@ struct MmaCtx {
     uint64_t done[DWM_MAX_STAGES];      // all compute warps have finished the tile (outputs written in place)
 };
 
-// mbarrier wait that lets the hardware park the thread (suspend-time hint, ns) instead of re-issuing try_wait in a
-// tight loop: the waiting TMA lanes must not steal issue slots from the compute warps of this 1-CTA-per-SM kernel.
-__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0, spins = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
-            : "memory");
-        if (++spins > (1u << 22)) __trap();
-    }
-}
-
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2,
                                          const uint32_t a3, const uint32_t b0, const uint32_t b1) {
     asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

@@ -187,6 +187,30 @@ __global__ void fold_gate_kernel(const float* __restrict__ W, const float* __res
     *reinterpret_cast<uint4*>(dst + idx * 8) = o;
 }
 
+// Transposed twin for the input-gradient GEMM of a squeeze-excite block: dst[b][k][n] = W[n][k] * gate[b][k]
+// (W fp32 [N][K] as stored by the layer, dst bf16 [B][K][N]): the gate scales the ROWS of the transposed weight,
+// i.e. the output columns of  dy2 = dz W  -- folded here so that GEMM needs no per-column epilogue vector.
+__global__ void fold_gate_t_kernel(const float* __restrict__ W, const float* __restrict__ gate,
+                                   __nv_bfloat16* __restrict__ dst, int N, int K, long long total8) {
+    pdl_trigger();
+    pdl_wait();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total8) return;
+    const int N8 = N >> 3;
+    const int n = (int)(idx % N8) << 3;
+    const long long q = idx / N8;
+    const int k = (int)(q % K);
+    const int b = (int)(q / K);
+    const float g = __ldg(gate + (long long)b * K + k);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(W + (long long)(n + i) * K + k) * g;
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst + idx * 8) = o;
+}
+
 // dst[(i*N + n)][(j*K + k)] = (i == j) ? W[n][k] : 0  -- the weight of a row-folded GEMM (pwgemm_tc.cu)
 __global__ void block_diag_kernel(const __nv_bfloat16* __restrict__ W, __nv_bfloat16* __restrict__ dst, int F, int N,
                                   int K, long long total) {
@@ -270,6 +294,16 @@ extern "C" int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, i
     (void)launch_pdl(fold_gate_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, W, gate,
                      (__nv_bfloat16*)dst, N, K, n);
     PB_CHECK_LAUNCH("fold_gate_kernel");
+    return PB_OK;
+}
+
+extern "C" int pb_fold_gate_t_bf16(const float* W, const float* gate, void* dst, int Bt, int N, int K, pb_stream_t stream) {
+    PB_REQUIRE(W && gate && dst && Bt > 0 && N > 0 && K > 0 && N % 8 == 0, "fold_gate_t: bad args (N must be a multiple of 8)");
+    PB_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "fold_gate_t: dst must be 16-byte aligned");
+    long long n = (long long)Bt * K * (N / 8);
+    (void)launch_pdl(fold_gate_t_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, W, gate,
+                     (__nv_bfloat16*)dst, N, K, n);
+    PB_CHECK_LAUNCH("fold_gate_t_kernel");
     return PB_OK;
 }
 

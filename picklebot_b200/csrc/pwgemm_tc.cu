@@ -17,6 +17,7 @@
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-7 and 8-11 = two epilogue groups, one per accumulator stage (warp w owns TMEM lanes 32*(w%4)..+31).
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -54,6 +55,7 @@ struct GemmParams {
     const float* bias;
     const float* colscale;
     const float* coladd;
+    const float* tinit;  // per-sample additive vector [Bt][N] applied by PRE-LOADING the accumulator (see the epilogue warps)
     __nv_bfloat16* C;
     double* stats;     // optional BatchNorm statistics of C: [PB_STAT_REPLICAS][2][stat_mod] sums of x and x^2
     int stat_mod;      // real channel count (column c of a row-folded problem is channel c % stat_mod)
@@ -132,7 +134,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
                 const int a = (int)(it & 1);
                 const uint32_t aph = (uint32_t)((it >> 1) & 1);
-                mbar_wait(&tempty_bar[a], aph ^ 1);
+                // tinit: the epilogue group pre-loads the accumulator and arrives once more up front, so the n-th use
+                // of a stage waits for its n-th completion instead of finding the first one free
+                mbar_wait(&tempty_bar[a], p.tinit ? aph : aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * acc_cols);
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -145,7 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint64_t adesc = make_desc(sa + sub * A_SUB_BYTES, 16, 8 * pitch, layout);
                         for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes = 2 descriptor units
                             umma_bf16(d_tmem + (uint32_t)(sub * p.block_n), adesc + (uint64_t)(2 * k),
-                                      bdesc + (uint64_t)(2 * k), idesc, (kc | k) != 0);
+                                      bdesc + (uint64_t)(2 * k), idesc, ((kc | k) != 0) || p.tinit != nullptr);
                     }
                     umma_commit(&empty_bar[s]);             // frees the smem slot when these MMAs retire
                     if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -166,6 +170,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int pi = 0; pi < (STATS ? 4 : 1); ++pi)
 #pragma unroll
             for (int i = 0; i < 8; ++i) { st_sum[pi][i] = 0.f; st_sq[pi][i] = 0.f; }
+        // tinit: write the per-sample additive vector of tile t into every row of accumulator stage `a` (each warp its
+        // 32 TMEM lanes), so that the MMAs accumulate on top of it and the plain bf16 epilogue below serves the call
+        auto preload = [&](long long t, int a) {
+            const int n_tile = (int)(t % p.n_tiles);
+            const int b = (int)((t / p.n_tiles) / p.m_tiles);
+            const float* src = p.tinit + (long long)b * p.N + n_tile * p.block_n;
+            const int ncols = min(p.block_n, p.N - n_tile * p.block_n);
+            for (int sub = 0; sub < p.mt; ++sub) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_cols + sub * p.block_n);
+                int c0 = 0;
+                for (; c0 + 16 <= p.block_n; c0 += 16) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c0 + j < ncols) f = __ldg(reinterpret_cast<const float4*>(src + c0 + j));
+                        v[j] = __float_as_uint(f.x); v[j + 1] = __float_as_uint(f.y);
+                        v[j + 2] = __float_as_uint(f.z); v[j + 3] = __float_as_uint(f.w);
+                    }
+                    tmem_st16(taddr + (uint32_t)c0, v);
+                }
+                if (c0 < p.block_n) {                                   // block_n is a multiple of 8
+                    uint32_t v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j += 4) {
+                        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c0 + j < ncols) f = __ldg(reinterpret_cast<const float4*>(src + c0 + j));
+                        v[j] = __float_as_uint(f.x); v[j + 1] = __float_as_uint(f.y);
+                        v[j + 2] = __float_as_uint(f.z); v[j + 3] = __float_as_uint(f.w);
+                    }
+                    tmem_st8(taddr + (uint32_t)c0, v);
+                }
+            }
+            tmem_st_wait();
+        };
+        if (p.tinit) {
+            const long long t0 = (long long)blockIdx.x + (long long)group * gridDim.x;
+            if (t0 < p.total_tiles) {
+                preload(t0, group);
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[group]);
+            }
+        }
         long long it = 0;
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int a = (int)(it & 1);
@@ -334,6 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                 }
             }
+            if (p.tinit && t + 2LL * gridDim.x < p.total_tiles) preload(t + 2LL * gridDim.x, a);
             tc_fence_before();
             mbar_arrive(&tempty_bar[a]);
         }
@@ -414,6 +462,11 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     const int stage_bytes = p.w_resident ? p.mt * BM * BK * 2 : (p.mt * BM + p.block_n) * BK * 2;
     p.stages = std::min(MAX_STAGES, (RING_BYTES - (p.w_resident ? wres_bytes : 0)) / stage_bytes);
     PB_REQUIRE(p.stages >= 2, "pw_gemm_tc: internal tiling error");
+    // A per-sample additive vector alone does not need the fp32 epilogue: the accumulator is pre-loaded with it
+    // (tcgen05.st by the epilogue warps) and the bf16 panel path stores the result.  PB_GEMM_NO_TINIT=1 keeps the
+    // old route for A/B tests.
+    p.tinit = nullptr;
+    if (coladd && !bias && !colscale && !stats && !getenv("PB_GEMM_NO_TINIT")) { p.tinit = coladd; coladd = nullptr; }
     p.bias = bias; p.colscale = colscale; p.coladd = coladd; p.C = (__nv_bfloat16*)C;
     p.stats = stats; p.stat_mod = stat_mod;
     if (stats) {

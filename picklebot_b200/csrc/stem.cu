@@ -186,12 +186,13 @@ static int stem_check(const StemDims& d) {
 // tcgen05 path (stem_tc.cu): bf16 activations, RGB channels-last clip, 3x3 spatial kernel, 16 output channels
 static bool stem_tc_eligible(const StemDims& d, int y_dtype) {
     return y_dtype == PB_BF16 && d.Cin == 3 && d.Cout == STEM_COUT && d.kH == 3 && d.kW == 3 && (d.kT == 3 || d.kT == 1) &&
-           d.xs_c == 1 && d.xs_w == 3;
+           d.xs_c == 1 && d.xs_w == 3 && d.in_scale == 255.f;
 }
 static StemTc stem_tc_dims(const StemDims& d) {
     StemTc t{d.B, d.T, d.H, d.W, d.To, d.Ho, d.Wo, d.sT, d.sH, d.sW, d.pT, d.pH, d.pW, d.xs_b, d.xs_t, d.xs_h, 0, 0};
     t.P = (long long)d.B * d.To * d.Ho * d.Wo;
     t.steps = (t.P + 255) / 256;
+    t.inv_scale = 1.0f / d.in_scale;
     return t;
 }
 

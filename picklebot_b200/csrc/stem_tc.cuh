@@ -10,6 +10,7 @@ struct StemTc {
     long long xs_b, xs_t, xs_h;       // element strides of the clip (channel stride 1, pixel stride 3)
     long long P;                      // output pixels
     long long steps;                  // 256-pixel steps
+    float inv_scale;                  // uint8 clips: 1 / in_scale (train.py:106's /255)
 };
 
 // Return true if they launched; false = not covered (caller uses the direct kernels).

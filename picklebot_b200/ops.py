@@ -114,6 +114,16 @@ def fold_gate(W: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def fold_gate_t(W: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
+    """bf16 [B][K][N] = W[n][k] * gate[b][k]: the per-sample weights of the input-gradient GEMM  dy2 = (dz W) * gate."""
+    _f32(W, "fold_gate_t.W"); _f32(gate, "fold_gate_t.gate")
+    N, K = W.shape[0], W.shape[1]
+    B = gate.shape[0]
+    dst = torch.empty((B, K, N), dtype=torch.bfloat16, device=W.device)
+    call("pb_fold_gate_t_bf16", W.data_ptr(), gate.data_ptr(), dst.data_ptr(), B, N, K, _st())
+    return dst
+
+
 # ---------------------------------------------------------------------------------------------
 # depthwise conv
 # ---------------------------------------------------------------------------------------------

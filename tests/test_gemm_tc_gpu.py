@@ -48,6 +48,32 @@ def test_gemm_tc_per_sample_weights(case):
     assert rel_err(C.float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("case", [(2, 931, 160, 960), (3, 3528, 112, 672), (64, 49, 96, 576), (5, 300, 40, 120),
+                                  (2, 1000, 40, 72), (1, 50, 24, 64), (400, 130, 80, 480)])
+def test_gemm_tc_se_input_gradient(case, monkeypatch):
+    """dy2 = (dz W) * gate + dmean of a squeeze-excite block (blocks.se_pw2_backward): the gate folded into the rows
+    of per-sample transposed weights (pb_fold_gate_t_bf16), dmean pre-loaded into the TMEM accumulator by the
+    epilogue warps (coladd alone) -- against fp32 math and against the fp32 epilogue-vector route it replaces.
+    The last case has more tiles than 2 x 148, so every accumulator stage is re-loaded several times."""
+    from picklebot_b200 import gemm_tc, ops
+    Bt, R, Cout, Cexp = case
+    dz = rnd(Bt * R, Cout, seed=1).bfloat16()
+    W = rnd(Cout, Cexp, seed=2, scale=0.3)                   # the layer's weight [N = Cout][K = Cexp]
+    gate = rnd(Bt, Cexp, seed=3).abs() + 0.1
+    dmean = rnd(Bt, Cexp, seed=4, scale=2.0)
+    Wtg = ops.fold_gate_t(W, gate)
+    assert Wtg.shape == (Bt, Cexp, Cout)
+    assert rel_err(Wtg.float(), W.t()[None] * gate[:, :, None]) < 4e-3
+    dy2 = gemm_tc.gemm(dz, Wtg, Cexp, Cout, Bw=Bt, Bt=Bt, coladd=dmean)
+    ref = (torch.einsum("bro,oe->bre", dz.float().view(Bt, R, Cout), W) * gate[:, None, :] + dmean[:, None, :]).reshape(-1, Cexp)
+    assert rel_err(dy2.float(), ref) < 6e-3
+    old = gemm_tc.gemm(dz, W.t().contiguous().bfloat16(), Cexp, Cout, Bw=1, Bt=Bt, colscale=gate, coladd=dmean)
+    assert rel_err(dy2.float(), old.float()) < 6e-3
+    monkeypatch.setenv("PB_GEMM_NO_TINIT", "1")              # same call through the fp32 epilogue
+    alt = gemm_tc.gemm(dz, Wtg, Cexp, Cout, Bw=Bt, Bt=Bt, coladd=dmean)
+    assert rel_err(dy2.float(), alt.float()) < 3e-3
+
+
 @pytest.mark.parametrize("case", [(4000, 16, 16, 4), (4000, 16, 64, 4), (1002, 24, 72, 2), (6000, 32, 96, 2)])
 def test_gemm_tc_row_folded(case):
     """K <= 32 layers run as X'[rows/F][F*K] against diag(W, ..., W) (pb_block_diag_bf16): same bytes out."""

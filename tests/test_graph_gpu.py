@@ -98,8 +98,8 @@ def test_graphed_step_matches_eager(model, autocast, monkeypatch):
             with torch.no_grad():
                 for m in (m_e, m_e2, m_g):
                     for p in m.parameters():
-                        if p.dim() > 1:
-                            p.mul_(0.9)
+                        if p.dim() > 1:                  # not a rescaling: BatchNorm makes the nets blind to those
+                            p.view(-1).add_(p.view(-1).roll(1), alpha=0.3)
         else:
             assert max(abs(a - b) for a, b in zip(first_losses, l_g)) > 10 * max(d_l, 1e-4)    # it did follow
     sd_e, sd_g = m_e.state_dict(), m_g.state_dict()

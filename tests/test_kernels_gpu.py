@@ -317,6 +317,49 @@ def test_stem_fwd_wgrad(conv, src, dt):
         assert rel_err(db, br.grad) < (1e-4 if dt == torch.float32 else 2e-3)
 
 
+@pytest.mark.parametrize("conv", [((3, 3, 3), (2, 2, 2), (1, 1, 1), True), ((1, 3, 3), (1, 2, 2), (0, 1, 1), False),
+                                  ((3, 3, 3), (1, 1, 1), (1, 1, 1), True)], ids=["mobilenet", "movinet", "stride1"])
+@pytest.mark.parametrize("shape", [(2, 6, 64, 64), (3, 5, 44, 48), (1, 4, 224, 224), (2, 3, 30, 16)],
+                         ids=["64x64", "ragged_row_groups", "224x224", "narrow"])
+def test_stem_tma_path(conv, shape, monkeypatch):
+    """uint8 clips whose rows are 16-byte multiples go through the TMA-staged tcgen05 stem (stem_tc.cu, round 2):
+    exact integer inputs, fp16 weights, /255 behind the accumulator.  Checked against fp32 convolution of the exact
+    x/255 with the fp16-rounded weights (forward: only the bf16 output rounding is left) and, for the weight
+    gradient, with the same bf16 upstream gradient (nothing is rounded before the products).  The gather kernels
+    (PB_STEM_GATHER=1) must agree with it to bf16 input-rounding accuracy."""
+    from picklebot_b200 import _lib, ops
+    k, s, p, has_bias = conv
+    B, T, H, W = shape
+    g = torch.Generator().manual_seed(1)
+    u8 = torch.randint(0, 256, (B, T, H, W, 3), generator=g, dtype=torch.uint8).cuda()
+    x = u8.permute(0, 4, 1, 2, 3)
+    w = rnd(16, 3, *k, seed=2, scale=0.3)
+    bias = rnd(16, seed=3) if has_bias else None
+    _lib.path_reset()
+    y = ops.stem_fwd(x, w, bias, k, s, p, torch.bfloat16)
+    xr = x.float() / 255
+    wr = w.half().float().requires_grad_(True)
+    br = bias.clone().requires_grad_(True) if has_bias else None
+    yr = F.conv3d(xr, wr, br, s, p)
+    assert rel_err(y.float(), yr.permute(0, 2, 3, 4, 1)) < 3e-3
+    dy = rnd(*y.shape, dt=torch.bfloat16, seed=4)
+    yr.backward(dy.float().permute(0, 4, 1, 2, 3))
+    dw, db = ops.stem_wgrad(x, dy, w.shape, k, s, p, has_bias)
+    tma = 2 if y.shape[3] <= 128 else 0                      # wider output rows stay on the gather kernels
+    # TMA path: exact inputs, what is left is the tensor core's fp32 accumulation over ~1e5 pixels per accumulator;
+    # gather path: x/255 rounded to bf16 first
+    assert rel_err(dw, wr.grad) < (5e-4 if tma else 3e-3)
+    if has_bias:
+        assert rel_err(db, br.grad) < 1e-4
+    c = _lib.path_counts()
+    assert c["stem_tma"] == tma and c["stem_tc"] == 2 and c["stem_simt"] == 0, c
+    monkeypatch.setenv("PB_STEM_GATHER", "1")
+    y2 = ops.stem_fwd(x, w, bias, k, s, p, torch.bfloat16)
+    dw2, _ = ops.stem_wgrad(x, dy, w.shape, k, s, p, has_bias)
+    assert _lib.path_counts()["stem_tma"] == tma
+    assert rel_err(y2.float(), y.float()) < 1e-2 and rel_err(dw2, dw) < 2e-3
+
+
 def test_errors_are_loud():
     from picklebot_b200 import _lib, ops
     x = torch.zeros(1, 2, 2, 2, 12, device="cuda")           # C=12 is not a multiple of 8

@@ -78,7 +78,12 @@ def test_eval_bf16_autocast_and_uint8_input(model):
     # is: within 1e-2 of the fp32 reference, or at least as close to it as the reference's own bf16 path
     assert e_mine < max(1e-2, 1.1 * e_ref)
     assert rel_err(mine, ref.float()) < max(1e-2, 2.0 * e_ref)
-    assert rel_err(mine_u8, mine) < 1e-2     # same inputs; fp32 atomics reorder -> bf16 rounding flips
+    # the raw uint8 path feeds the stem EXACT pixel values (integers, /255 behind the accumulator) where train.py:106's
+    # feature tensor is x/255 rounded to bf16: it sits closer to the fp32 truth and a bf16 input rounding away from `mine`
+    e_u8 = rel_err(mine_u8, truth)
+    print(f"{model}: uint8 path vs fp32 reference {e_u8:.2e}, vs the bf16-feature path {rel_err(mine_u8, mine):.2e}")
+    assert e_u8 < max(1e-2, 1.1 * e_ref)
+    assert rel_err(mine_u8, mine) < max(2e-2, 2.0 * e_ref)
     assert torch.equal(mine.argmax(1).cpu(), truth.argmax(1))
     assert torch.equal(mine_u8.argmax(1).cpu(), truth.argmax(1))
 
