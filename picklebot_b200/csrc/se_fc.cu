@@ -13,10 +13,54 @@ namespace pb {
 
 constexpr int FC_BT = 8;       // samples per CTA; their input vectors are staged in shared memory
 
+// The weights of these layers are parameters: nothing in flight writes them, but by the time a layer runs again they
+// have long left L2.  Each CTA asks for its slice BEFORE griddepcontrol.wait, i.e. while the kernel that produces
+// its inputs is still running (PDL), so the cold misses overlap that kernel instead of heading a latency chain.
+__device__ __forceinline__ void prefetch_rows_l2(const float* base, int rows, long long row_stride, int row_floats) {
+    const int lines = (row_floats * 4 + 127) >> 7;
+    for (int i = threadIdx.x; i < rows * lines; i += blockDim.x) {
+        const int r = i / lines, l = i - r * lines;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (long long)r * row_stride + l * 32));
+    }
+}
+
+// The FC_BT input rows are contiguous in X ([B][K] row-major), so the staging is one flat copy.  Loads are issued
+// four at a time into registers BEFORE the stores: with one load in flight per thread this loop was a 20 us
+// latency chain for K = 960 (ncu: fc_rows 24.5 us, of which the products are ~2 us).
 __device__ __forceinline__ void stage_x(const float* __restrict__ X, float* xs, int b0, int B, int K) {
-    for (int i = threadIdx.x; i < FC_BT * K; i += blockDim.x) {
-        const int bi = i / K, k = i - bi * K;
-        xs[i] = (b0 + bi < B) ? __ldg(X + (long long)(b0 + bi) * K + k) : 0.f;
+    const int nb = min(FC_BT, B - b0);
+    const int n = nb * K, total = FC_BT * K;
+    const float* src = X + (long long)b0 * K;
+    const int nt = blockDim.x;
+    if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int n4 = n >> 2, t4 = total >> 2;
+        for (int base = threadIdx.x; base < t4; base += 4 * nt) {
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = base + j * nt;
+                v[j] = i < n4 ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = base + j * nt;
+                if (i < t4) reinterpret_cast<float4*>(xs)[i] = v[j];
+            }
+        }
+    } else {
+        for (int base = threadIdx.x; base < total; base += 8 * nt) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = base + j * nt;
+                v[j] = i < n ? __ldg(src + i) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = base + j * nt;
+                if (i < total) xs[i] = v[j];
+            }
+        }
     }
     __syncthreads();
 }
@@ -28,6 +72,7 @@ __global__ void __launch_bounds__(256)
 fc_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
                float* __restrict__ Y, int B, int N, int K) {
     pdl_trigger();
+    prefetch_rows_l2(W + (long long)blockIdx.x * 32 * K, min(32, N - (int)blockIdx.x * 32), K, K);
     pdl_wait();
     extern __shared__ float xs[];                       // [FC_BT][K]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -39,10 +84,31 @@ fc_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, const f
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int i = 0; i < FC_BT; ++i) acc[j][i] = 0.f;
-    for (int k = lane; k < K; k += 32) {
+    // weights are cold (HBM) in a training step and this kernel is a latency chain: 16 loads per lane are issued
+    // before the first product (the compiler would not batch them across the loop's bounds checks on its own)
+    const float* wrow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wrow[j] = W + (long long)min(n0 + j, N - 1) * K;
+    int k = lane;
+    for (; k + 96 < K; k += 128) {
+        float wv[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[u][j] = __ldg(wrow[j] + k + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < FC_BT; ++i) {
+                const float xv = xs[i * K + k + 32 * u];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(xv, wv[u][j], acc[j][i]);
+            }
+    }
+    for (; k < K; k += 32) {
         float wv[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) wv[j] = (n0 + j < N) ? __ldg(W + (long long)(n0 + j) * K + k) : 0.f;
+        for (int j = 0; j < 4; ++j) wv[j] = __ldg(wrow[j] + k);
 #pragma unroll
         for (int i = 0; i < FC_BT; ++i) {
             const float xv = xs[i * K + k];
@@ -74,6 +140,7 @@ __global__ void __launch_bounds__(256)
 fc_cols_kernel(const float* __restrict__ X, const float* __restrict__ Wt, const float* __restrict__ relu_ref,
                float* __restrict__ Y, int B, int N, int K, float scale) {
     pdl_trigger();
+    prefetch_rows_l2(Wt + blockIdx.x * 32, K, N, min(32, N - (int)blockIdx.x * 32));
     pdl_wait();
     extern __shared__ float xs[];                       // [FC_BT][K] | red[8][FC_BT][33]
     float* red = xs + FC_BT * K;
@@ -85,7 +152,17 @@ fc_cols_kernel(const float* __restrict__ X, const float* __restrict__ Wt, const 
 #pragma unroll
     for (int i = 0; i < FC_BT; ++i) acc[i] = 0.f;
     if (n < N) {
-        for (int k = ks; k < K; k += 8) {
+        int k = ks;
+        for (; k + 56 < K; k += 64) {                       // eight weight rows in flight per thread
+            float wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wv[u] = __ldg(Wt + (long long)(k + 8 * u) * N + n);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int i = 0; i < FC_BT; ++i) acc[i] = fmaf(xs[i * K + k + 8 * u], wv[u], acc[i]);
+        }
+        for (; k < K; k += 8) {
             const float wv = __ldg(Wt + (long long)k * N + n);
 #pragma unroll
             for (int i = 0; i < FC_BT; ++i) acc[i] = fmaf(xs[i * K + k], wv, acc[i]);
@@ -150,7 +227,8 @@ se_fc_bwd_param_kernel(const float* __restrict__ a2, const float* __restrict__ a
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     }
     for (int b0 = 0; b0 < B; b0 += BC) {
-        for (int e = threadIdx.x; e < BC * 64; e += 256) {
+#pragma unroll
+        for (int e = threadIdx.x; e < BC * 64; e += 256) {      // 8 iterations: all 16 loads of a thread in flight
             const int bi = e >> 6, k = e & 63, b = b0 + bi;
             xs[bi][k] = (b < B && r0 + k < Rn) ? __ldg(X + (long long)b * Rn + r0 + k) : 0.f;
             ys[bi][k] = (b < B && c0 + k < Cn) ? __ldg(Y + (long long)b * Cn + c0 + k) : 0.f;

@@ -44,9 +44,10 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, ui
 struct P {
     int B, T, H, W, C, Cb, Hi, Wi, Ht, Wt, pad, stages, stage_bytes, nblk, tiles_h, tiles_w;
     long long ntiles;
+    int nprod;     // TMA-issuing threads per CTA (one per warp), tiles dealt round-robin
 };
 
-__global__ void __launch_bounds__(64) tma_stream_kernel(const __grid_constant__ CUtensorMap tm, const P p, unsigned* sink) {
+__global__ void __launch_bounds__(160) tma_stream_kernel(const __grid_constant__ CUtensorMap tm, const P p, unsigned* sink) {
     extern __shared__ uint8_t raw[];
     __shared__ uint64_t full[8], empty[8];
     const uint32_t a = smem_u32(raw);
@@ -58,8 +59,8 @@ __global__ void __launch_bounds__(64) tma_stream_kernel(const __grid_constant__ 
     __syncthreads();
     const long long mine = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int c_base = blockIdx.y * p.Cb;
-    if (threadIdx.x == 32) {
-        for (long long n = 0; n < mine; ++n) {
+    if (threadIdx.x >= 32 && (threadIdx.x & 31) == 0 && (int)(threadIdx.x >> 5) - 1 < p.nprod) {
+        for (long long n = (threadIdx.x >> 5) - 1; n < mine; n += p.nprod) {
             const int s = (int)(n % p.stages);
             if (n >= p.stages) mbar_wait(&empty[s], (uint32_t)(((n / p.stages) - 1) & 1));
             long long t = blockIdx.x + n * (long long)gridDim.x;
@@ -91,8 +92,9 @@ static EncodeTiledFn enc() {
 }
 
 static void run(const char* name, int B, int T, int H, int W, int C, int Cb, int Ht, int Wt, int K, int swz, int ctas_per_sm,
-                int stages, void* buf, unsigned* sink) {
+                int stages, void* buf, unsigned* sink, int nprod = 1) {
     P p{};
+    p.nprod = nprod;
     p.B = B; p.T = T; p.H = H; p.W = W; p.C = C; p.Cb = Cb; p.Ht = Ht; p.Wt = Wt; p.pad = K / 2;
     p.Hi = Ht + K - 1; p.Wi = Wt + K - 1;
     p.stages = stages;
@@ -121,7 +123,7 @@ static void run(const char* name, int B, int T, int H, int W, int C, int Cb, int
     float best = 1e30f;
     for (int it = 0; it < 5; ++it) {
         CK(cudaEventRecord(e0));
-        tma_stream_kernel<<<grid, 64, smem>>>(tm, p, sink);
+        tma_stream_kernel<<<grid, 32 + 32 * nprod, smem>>>(tm, p, sink);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -132,8 +134,8 @@ static void run(const char* name, int B, int T, int H, int W, int C, int Cb, int
     const double boxb = (double)p.ntiles * p.nblk * p.Hi * p.Wi * Cb * 2;
     const double rows = (double)p.ntiles * p.nblk * p.Hi * p.Wi;
     const double clk = best * 1e-3 * 1.9e9;   // ~SM cycles
-    printf("%-34s Cb=%3d box %2dx%2d rowB=%3d swz=%3d %dcta/SM st=%d | %7.1f us | unique %6.0f GB/s | box %6.0f GB/s | %5.2f clk/row/SM\n",
-           name, Cb, p.Hi, p.Wi, Cb * 2, swz, ctas_per_sm, stages, best * 1000, uniq / best / 1e6, boxb / best / 1e6,
+    printf("%-34s Cb=%3d box %2dx%2d rowB=%3d swz=%3d %dcta/SM st=%d np=%d | %7.1f us | unique %6.0f GB/s | box %6.0f GB/s | %5.2f clk/row/SM\n",
+           name, Cb, p.Hi, p.Wi, Cb * 2, swz, ctas_per_sm, stages, nprod, best * 1000, uniq / best / 1e6, boxb / best / 1e6,
            clk / (rows / 148.0));
 }
 
@@ -141,6 +143,14 @@ int main() {
     const size_t bytes = (size_t)1 << 30;
     void* buf; unsigned* sink;
     CK(cudaMalloc(&buf, bytes)); CK(cudaMemset(buf, 1, bytes)); CK(cudaMalloc(&sink, 4));
+    if (getenv("TMA_BENCH_NPROD")) {   // does a CTA move more box rows per clock when several of its threads issue the loads?
+        for (int np : {1, 2, 4})
+            for (int cb : {32, 64, 128})
+                run("producers per CTA C=256", 64, 8, 28, 28, 256, cb, 7, 14, 3, 0, 1, 4, buf, sink, np);
+        for (int np : {1, 2, 4})
+            run("producers per CTA swz128", 64, 8, 28, 28, 256, 64, 7, 14, 3, 128, 1, 4, buf, sink, np);
+        return 0;
+    }
     // row-size sweep on a 256-channel tensor, 3x3 halo, 7x14 tiles; then ring depth / CTAs per SM at fixed row sizes
     for (int cb : {16, 32, 64, 128, 256})
         run("sweep C=256 28x28 T=8 B=64", 64, 8, 28, 28, 256, cb, 7, 14, 3, 0, 1, 2, buf, sink);
