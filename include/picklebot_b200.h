@@ -61,6 +61,13 @@ int pb_dwconv3d_fwd(const void* x, const float* w_tc, void* y, int dtype,
                     int B, int C, int T, int H, int W, int kT, int kH, int kW,
                     int sT, int sH, int sW, int pT, int pH, int pW, int To, int Ho, int Wo,
                     pb_stream_t stream);
+/* The same forward plus the global average pool of its output (SEBlock3D's AdaptiveAvgPool3d, mobilenet.py:15-16,84-88)
+ * in the same pass: pool[B][C] fp32 = mean over (To,Ho,Wo) of the stored (rounded) outputs.  The TMA strip kernels
+ * accumulate it while storing; shapes they decline are pooled by a second pass (pb_pool_fwd).  pool need not be zeroed. */
+int pb_dwconv3d_fwd_pool(const void* x, const float* w_tc, void* y, float* pool, int dtype,
+                    int B, int C, int T, int H, int W, int kT, int kH, int kW,
+                    int sT, int sH, int sW, int pT, int pH, int pW, int To, int Ho, int Wo,
+                    pb_stream_t stream);
 int pb_dwconv3d_dgrad(const void* dy, const float* w_tc, void* dx, int dtype,
                       int B, int C, int T, int H, int W, int kT, int kH, int kW,
                       int sT, int sH, int sW, int pT, int pH, int pW, int To, int Ho, int Wo,

@@ -23,6 +23,7 @@ _T = {"p": _P, "i": _I, "l": _L, "f": _F}
 _DW = "pppi" + "i" * 17 + "p"
 SIGNATURES = {
     "pb_dwconv3d_fwd": _DW,
+    "pb_dwconv3d_fwd_pool": "ppppi" + "i" * 17 + "p",
     "pb_dwconv3d_dgrad": _DW,
     "pb_dwconv3d_wgrad": _DW,
     "pb_stream_dwconv3d_fwd": "pppppi" + "i" * 14 + "p",

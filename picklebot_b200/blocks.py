@@ -217,11 +217,13 @@ class BottleneckFn(torch.autograd.Function):
         dt = x5.dtype
         y1 = pw_fwd(x5.view(-1, Cin), w1, cache, "w1").view(B, T, H, W, Cexp)
         wdw_tc = cache.get(("wdw", dt), wdw, lambda: ops.dw_weight_tapmajor(wdw, dt))
-        y2 = ops.dwconv_fwd(y1, wdw_tc, cfg.k, cfg.s, cfg.p)
-        _, To, Ho, Wo, _ = y2.shape
         pooled = hidden = gate = None
+        if cfg.use_se:      # the squeeze (average pool) rides on the depthwise kernel's output stores
+            y2, pooled = ops.dwconv_fwd_pool(y1, wdw_tc, cfg.k, cfg.s, cfg.p)
+        else:
+            y2 = ops.dwconv_fwd(y1, wdw_tc, cfg.k, cfg.s, cfg.p)
+        _, To, Ho, Wo, _ = y2.shape
         if cfg.use_se:
-            pooled = ops.pool_fwd(y2, B, Cexp)
             hidden, gate = ops.se_fc_fwd(pooled, _w2d(se_w1), se_b1.detach(), _w2d(se_w2), se_b2.detach())
         z, zsums = pw_fwd(y2.view(-1, Cexp), w2, cache, "w2", gate=gate, Bt=B if gate is not None else 1,
                           want_stats=True, fuse_stats=training or rmean is None)

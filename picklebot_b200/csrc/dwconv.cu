@@ -6,6 +6,8 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include <cstdlib>
+
 #include "dwconv.cuh"
 
 namespace pb {
@@ -217,6 +219,28 @@ extern "C" int pb_dwconv3d_fwd(const void* x, const float* w_tc, void* y, int dt
     PB_CHECK_LAUNCH("dw_fwd_generic");
     count_path(PB_PATH_DW_FWD_GENERIC);
     return PB_OK;
+}
+
+extern "C" int pb_pool_fwd(const void* x, int dtype, int B, long long R, int C, float* mean, pb_stream_t stream);
+
+// Forward + global average pool of the output in one pass (squeeze-excite blocks, mobilenet.py:84-88): the strip
+// kernels add the rounded outputs into pool[B][C] while they store them; every other path pools in a second pass.
+extern "C" int pb_dwconv3d_fwd_pool(const void* x, const float* w_tc, void* y, float* pool, int dtype, DW_ARGS,
+                                    pb_stream_t stream) {
+    DW_PACK;
+    if (int e = check_dims(d)) return e;
+    PB_REQUIRE(pool != nullptr, "dwconv3d_fwd_pool: null pool pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == PB_BF16 && !getenv("PB_DW_POOL_SEPARATE")) {
+        PB_CUDA(cudaMemsetAsync(pool, 0, sizeof(float) * (size_t)B * C, st));
+        if (dw_fwd_tiled<__nv_bfloat16>((const __nv_bfloat16*)x, w_tc, (__nv_bfloat16*)y, d, st, pool)) {
+            PB_CHECK_LAUNCH("dw_fwd_tiled(pool)");
+            count_path(PB_PATH_DW_FWD_TMA);
+            return PB_OK;
+        }
+    }
+    if (int e = pb_dwconv3d_fwd(x, w_tc, y, dtype, B, C, T_, H, W, kT, kH, kW, sT, sH, sW, pT, pH, pW, To, Ho, Wo, stream)) return e;
+    return pb_pool_fwd(y, dtype, B, (long long)To * Ho * Wo, C, pool, stream);
 }
 
 extern "C" int pb_dwconv3d_dgrad(const void* dy, const float* w_tc, void* dx, int dtype, DW_ARGS, pb_stream_t stream) {

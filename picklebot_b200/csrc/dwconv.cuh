@@ -12,7 +12,7 @@ struct DwDims {
 
 // Fast paths; each returns true if it handled (launched) the problem, false to fall through to the
 // general-shape kernel of the same library.
-template <typename T> bool dw_fwd_tiled(const T* x, const float* w_tc, T* y, const DwDims& d, cudaStream_t st);
+template <typename T> bool dw_fwd_tiled(const T* x, const float* w_tc, T* y, const DwDims& d, cudaStream_t st, float* pool = nullptr);
 template <typename T> bool dw_dgrad_tiled(const T* dy, const float* w_tc, T* dx, const DwDims& d, cudaStream_t st);
 template <typename T> bool dw_wgrad_tiled(const T* x, const T* dy, float* dw_tc, const DwDims& d, cudaStream_t st);
 

@@ -51,7 +51,22 @@ struct DwTile {
     int flip;
     int kT, padT;              // temporal taps (forward kernel only) and frames of padding before the first one
     int src_T, sbuf_T;         // frames of the source tensor / of the stream buffer (0: not streaming)
+    // forward only: fused global average pool of the outputs (squeeze-excite), pool[b][c] += pool_scale * y
+    float* pool;
+    float pool_scale;
+    int contig;                // tiles of a CTA are consecutive (few sample changes -> few pool flushes) instead of strided
 };
+
+// n-th tile of this CTA and how many it has
+__device__ __forceinline__ long long cta_tile(const DwTile& p, long long n) {
+    if (!p.contig) return blockIdx.x + n * (long long)gridDim.x;
+    const long long per = p.ntiles / gridDim.x, rem = p.ntiles % gridDim.x;
+    return blockIdx.x * per + (blockIdx.x < rem ? blockIdx.x : rem) + n;
+}
+__device__ __forceinline__ long long cta_tile_count(const DwTile& p) {
+    if (!p.contig) return p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    return p.ntiles / gridDim.x + (blockIdx.x < p.ntiles % gridDim.x ? 1 : 0);
+}
 
 __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
     unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
@@ -133,7 +148,7 @@ __device__ __forceinline__ void producer_loop(TileCtx& cx, const DwTile& p, uint
     for (long long n = 0; n < my_tiles; ++n) {
         const int s = (int)(n % p.stages);
         if (n >= p.stages) mbar_wait(&cx.empty[s], (uint32_t)(((n / p.stages) - 1) & 1));
-        const int4 c = decode_tile(p, blockIdx.x + n * (long long)gridDim.x);
+        const int4 c = decode_tile(p, cta_tile(p, n));
         cx.coord[s] = c;
         mbar_expect_tx(&cx.full[s], tx_bytes);          // release: publishes coord[s] as well
         load(ring + (size_t)s * p.stage_bytes, &cx.full[s], c);
@@ -172,7 +187,7 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
     pipeline_init(cx, p);
     pdl_wait();                 // barrier setup above overlaps the previous kernel's tail
     if constexpr (K == 5) stage_taps<K * K>(reinterpret_cast<float*>(ring + (size_t)p.stages * p.stage_bytes), w_tc, p, c_base, p.flip);
-    const long long my_tiles = p.ntiles > blockIdx.x ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long my_tiles = cta_tile_count(p);
 
     if (tid >= DWT_CONSUMERS) {
         if (tid == DWT_CONSUMERS) {
@@ -216,12 +231,26 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
     const uint32_t row_bytes = (uint32_t)(p.Wi * cb_bytes);
     const int lane = tid & 31;
 
+    // fused average pool: per-thread sums of the ROUNDED outputs of its 4 channels, flushed with one atomic per channel
+    // whenever the sample changes (tiles of a CTA are consecutive when p.pool is set: one or two flushes per CTA)
+    float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+    int pool_b = -1;
+    auto pool_flush = [&]() {
+        if (pool_b >= 0 && active) {
+            float* dst = p.pool + (long long)pool_b * p.C + c_base + g * 4;
+            atomicAdd(dst + 0, ps0 * p.pool_scale); atomicAdd(dst + 1, ps1 * p.pool_scale);
+            atomicAdd(dst + 2, ps2 * p.pool_scale); atomicAdd(dst + 3, ps3 * p.pool_scale);
+        }
+        ps0 = ps1 = ps2 = ps3 = 0.f;
+    };
+
     for (long long n = 0; n < my_tiles; ++n) {
         const int s = (int)(n % p.stages);
         mbar_wait(&cx.full[s], (uint32_t)((n / p.stages) & 1));
         const int4 c = cx.coord[s];
         const int to = p.f_first + c.y * p.f_step;
         const uint32_t tile = ring_u32 + (uint32_t)(s * p.stage_bytes) + (uint32_t)(g * 8);
+        if (p.pool && c.x != pool_b) { pool_flush(); pool_b = c.x; }
         if (active) {
             ItemIter it;
             it.start(slot, ppp, nstrips);
@@ -278,6 +307,10 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
                         out.x = pack_bf16x2(acc[o][0].x, acc[o][0].y);
                         out.y = pack_bf16x2(acc[o][1].x, acc[o][1].y);
                         *reinterpret_cast<uint2*>(yp) = out;
+                        if (p.pool) {
+                            ps0 += bf16_lo(out.x); ps1 += bf16_hi(out.x);
+                            ps2 += bf16_lo(out.y); ps3 += bf16_hi(out.y);
+                        }
                     }
                     yp += p.C;
                 }
@@ -286,6 +319,7 @@ dw_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restri
         __syncwarp();
         if (lane == 0) mbar_arrive(&cx.empty[s]);          // this warp is done reading stage s
     }
+    if (p.pool) pool_flush();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -758,13 +792,15 @@ static void set_smem_once(KernelT k, unsigned long long& done) {
 
 template <int K, int S, int WS>
 static bool launch_fwd(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y, const DwDims& d, int pT, int sT,
-                       int flip, cudaStream_t st) {
-    DwTile p;
+                       int flip, cudaStream_t st, float* pool = nullptr) {
+    DwTile p{};
     constexpr int TAPS_BYTES = K == 5 ? K * K * 128 * 4 : 0;           // fp32 [tap][Cb <= 128]
     PlanIn in{d.B, d.C, d.To, d.Ho, d.Wo, K, S, WS, d.pH, 0, TAPS_BYTES};
     if (!plan_tile(in, p)) return false;
     if (!plan_frames(p, d.To, d.T, sT, -pT, 1)) return false;      // source frame = to*sT - pT
     p.flip = flip;
+    p.pool = pool; p.contig = pool ? 1 : 0;
+    p.pool_scale = 1.0f / ((float)d.To * (float)d.Ho * (float)d.Wo);
     CUtensorMap tm;
     if (make_map5(&tm, x, d.C, d.W, d.H, d.T, d.B, p.Cb, p.Wi, p.Hi) != PB_OK) return false;
     static unsigned long long once = 0;
@@ -779,7 +815,7 @@ template <int K>
 static bool launch_dgrad_s2(const __nv_bfloat16* dy, const float* w_tc, __nv_bfloat16* dx, const DwDims& d,
                             cudaStream_t st) {
     constexpr int XS = 4;
-    DwTile p;
+    DwTile p{};
     constexpr int TAPS_BYTES = K == 5 ? K * K * 128 * 4 : 0;
     PlanIn in{d.B, d.C, d.T, d.H, d.W, K, 0, XS, d.pH, 0, TAPS_BYTES};
     if (!plan_tile(in, p)) return false;
@@ -797,7 +833,7 @@ static bool launch_dgrad_s2(const __nv_bfloat16* dy, const float* w_tc, __nv_bfl
 template <int K, int S, int WS>
 static bool launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw_tc, const DwDims& d,
                          cudaStream_t st) {
-    DwTile p;
+    DwTile p{};
     PlanIn in{d.B, d.C, d.To, d.Ho, d.Wo, K, S, WS, d.pH, 1, 0};
     if (!plan_tile(in, p)) return false;
     if (p.Gb * K > DWT_CONSUMERS) return false;
@@ -819,7 +855,7 @@ static bool launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float*
 template <int KT, int S, int WS>
 static bool launch_fwd3d(const __nv_bfloat16* x, const __nv_bfloat16* sbuf, const float* w_tc, __nv_bfloat16* y,
                          const DwDims& d, int padT, cudaStream_t st) {
-    DwTile p;
+    DwTile p{};
     constexpr int TAPS_BYTES = KT * 9 * 128 * 4;                            // fp32 [tap][Cb <= 128]
     PlanIn in{d.B, d.C, d.To, d.Ho, d.Wo, 3, S, WS, d.pH, 0, TAPS_BYTES};
     in.frames = KT;
@@ -870,19 +906,23 @@ static bool aligned16(const void* a, const void* b) {
 // strips of 7 fit the 112/56/28/14/7 widths of the 224x224 models exactly; 4 otherwise
 static bool strip7(int wo) { return wo % 7 == 0; }
 
+// pool != nullptr: also accumulate the global average pool of y into pool[B][C] (zeroed by the caller); only the
+// strip kernels do that, so the (kT,3,3) and tensor-core kernels decline and the caller pools separately.
 template <> bool dw_fwd_tiled<__nv_bfloat16>(const __nv_bfloat16* x, const float* w_tc, __nv_bfloat16* y,
-                                            const DwDims& d, cudaStream_t st) {
-    if (movinet3d_class(d) && aligned16(x, y) && d.pT == d.kT / 2)      // MoViNet's symmetric temporal padding
+                                            const DwDims& d, cudaStream_t st, float* pool) {
+    if (movinet3d_class(d) && aligned16(x, y) && d.pT == d.kT / 2) {    // MoViNet's symmetric temporal padding
+        if (pool) return false;
         return d.kT == 3 ? dispatch_fwd3d<3>(x, nullptr, w_tc, y, d, 1, st) : dispatch_fwd3d<5>(x, nullptr, w_tc, y, d, 2, st);
+    }
     if (!mobilenet_class(d) || !aligned16(x, y)) return false;
-    if (dw_fwd_mma(x, w_tc, y, d, st)) return true;            // stride 1: tensor-core kernel (dwconv_mma.cu)
+    if (!pool && dw_fwd_mma(x, w_tc, y, d, st)) return true;   // stride 1: tensor-core kernel (dwconv_mma.cu)
     if (d.kH == 3 && d.sH == 1)
-        return strip7(d.Wo) ? launch_fwd<3, 1, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st) : launch_fwd<3, 1, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
+        return strip7(d.Wo) ? launch_fwd<3, 1, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st, pool) : launch_fwd<3, 1, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st, pool);
     if (d.kH == 3 && d.sH == 2)
-        return strip7(d.Wo) ? launch_fwd<3, 2, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st) : launch_fwd<3, 2, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
+        return strip7(d.Wo) ? launch_fwd<3, 2, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st, pool) : launch_fwd<3, 2, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st, pool);
     if (d.kH == 5 && d.sH == 1)
-        return strip7(d.Wo) ? launch_fwd<5, 1, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st) : launch_fwd<5, 1, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
-    if (d.kH == 5 && d.sH == 2) return launch_fwd<5, 2, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st);
+        return strip7(d.Wo) ? launch_fwd<5, 1, 7>(x, w_tc, y, d, d.pT, d.sT, 0, st, pool) : launch_fwd<5, 1, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st, pool);
+    if (d.kH == 5 && d.sH == 2) return launch_fwd<5, 2, 4>(x, w_tc, y, d, d.pT, d.sT, 0, st, pool);
     return false;
 }
 
@@ -918,7 +958,7 @@ template <> bool dw_wgrad_tiled<__nv_bfloat16>(const __nv_bfloat16* x, const __n
     return false;
 }
 
-template <> bool dw_fwd_tiled<float>(const float*, const float*, float*, const DwDims&, cudaStream_t) { return false; }
+template <> bool dw_fwd_tiled<float>(const float*, const float*, float*, const DwDims&, cudaStream_t, float*) { return false; }
 template <> bool dw_dgrad_tiled<float>(const float*, const float*, float*, const DwDims&, cudaStream_t) { return false; }
 template <> bool dw_wgrad_tiled<float>(const float*, const float*, float*, const DwDims&, cudaStream_t) { return false; }
 

@@ -143,6 +143,18 @@ def dwconv_fwd(x: torch.Tensor, w_tc: torch.Tensor, k, s, p) -> torch.Tensor:
     return y
 
 
+def dwconv_fwd_pool(x: torch.Tensor, w_tc: torch.Tensor, k, s, p) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Depthwise forward + the global average pool of its output, fp32 [B][C], in the same pass (squeeze-excite)."""
+    _chk(x, "dwconv_fwd_pool.x")
+    d = _dw_dims(x.shape, k, s, p)
+    y = torch.empty((d[0], d[14], d[15], d[16], d[1]), dtype=x.dtype, device=x.device)
+    pooled = torch.empty((d[0], d[1]), dtype=torch.float32, device=x.device)
+    call("pb_dwconv3d_fwd_pool", x.data_ptr(), w_tc.data_ptr(), y.data_ptr(), pooled.data_ptr(), _dt(x), *d, _st(),
+         nbytes=(x.numel() + y.numel()) * x.element_size() + w_tc.numel() * x.element_size(),
+         wbytes=y.numel() * y.element_size())
+    return y, pooled
+
+
 def dwconv_dgrad(dy: torch.Tensor, w_tc: torch.Tensor, x_shape, k, s, p) -> torch.Tensor:
     _chk(dy, "dwconv_dgrad.dy")
     d = _dw_dims(x_shape, k, s, p)

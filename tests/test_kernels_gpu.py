@@ -74,6 +74,26 @@ def _is_mobilenet_class(k, s, p):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", DW_CASES + [(64, 120, 3, 28, 28, (1, 5, 5), (1, 1, 1), (1, 2, 2)),
+                                             (70, 672, 2, 14, 14, (1, 3, 3), (1, 1, 1), (1, 1, 1)),
+                                             (5, 72, 6, 20, 20, (1, 5, 5), (2, 2, 2), (1, 2, 2))])
+def test_dwconv_fwd_pool(case, dt):
+    """pb_dwconv3d_fwd_pool: the squeeze-excite average pool accumulated by the depthwise kernel while it stores its
+    outputs (strip kernels; other paths pool in a second pass) equals pooling the stored tensor."""
+    from picklebot_b200 import ops
+    B, C, T, H, W, k, s, p = case
+    x = rnd(B, T, H, W, C, dt=dt, seed=1)
+    w_tc = ops.dw_weight_tapmajor(rnd(C, 1, *k, seed=2, scale=0.5), dt)
+    y0 = ops.dwconv_fwd(x, w_tc, k, s, p)
+    y, pooled = ops.dwconv_fwd_pool(x, w_tc, k, s, p)
+    assert rel_err(y.float(), y0.float()) < 1e-4          # the tensor-core kernel may have served y0: a few 1-ulp bf16 flips
+    ref = y.float().mean(dim=(1, 2, 3))
+    assert pooled.shape == (B, C) and rel_err(pooled, ref) < 1e-5
+    assert rel_err(pooled, ops.pool_fwd(y, B, C)) < 1e-5
+
+
+
+@pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("case", DW_CASES)
 @pytest.mark.parametrize("mma", ["default", "forced"])
 def test_dwconv_fwd_dgrad_wgrad(case, dt, mma, monkeypatch):
