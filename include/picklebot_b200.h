@@ -113,6 +113,13 @@ int pb_pw_gemm_simt(const void* A, const float* W, long long w_sn, long long w_s
 int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const float* bias,
                   const float* colscale, const float* coladd, void* C, double* stats, int stat_mod,
                   int Bt, long long R, int K, int N, pb_stream_t stream);
+/* The same with an activation on the fp32 accumulators: C = act(A W^T + bias).  Inference form of
+ * conv -> BatchNorm(eval) -> activation (mobilenet.py:89-91 in eval mode) once the caller has folded the BatchNorm
+ * scale into W (pb_fold_scaled_bf16) and passes its shift as bias.  Needs the plain epilogue: no statistics, no
+ * colscale, at most one of bias / coladd (either one pre-loads the TMEM accumulator). */
+int pb_pw_gemm_tc_act(const void* A, const void* W_bf16, int Bw, const float* bias,
+                  const float* colscale, const float* coladd, void* C, double* stats, int stat_mod,
+                  int Bt, long long R, int K, int N, int act, float slope, pb_stream_t stream);
 /* Weight gradient  dW[n][k] = sum_b ascale[b][k] * sum_r dC[b][r][n] * A[b][r][k]  (fp32, overwritten).
  * Optionally also dbias[n] = sum dC (NULL to skip). */
 int pb_pw_wgrad_simt(const void* A, const void* dC, const float* ascale, float* dW, float* dbias,
@@ -134,6 +141,10 @@ int pb_cast_matrix(const float* src, void* dst, int dst_dtype, int rows, int col
 int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, int Bt, int N, int K, pb_stream_t stream);
 /* transposed twin for the input gradient  dy2 = (dz W) * gate  of the same block (blocks.py se_pw2_backward):
  * dst[b][k][n] = bf16(W[n][k] * gate[b][k]), W fp32 [N][K], gate fp32 [Bt][K], dst bf16 [Bt][K][N], N % 8 == 0. */
+/* inference: dst[b][n][k] = bf16(W[n][k] * gate[b][k] * rowscale[n]); gate (fp32 [Bt][K]) and rowscale (fp32 [N], the
+ * eval-mode BatchNorm scale of the layer's output channels) are each optional (NULL); without a gate Bt must be 1. */
+int pb_fold_scaled_bf16(const float* W, const float* gate, const float* rowscale, void* dst, int Bt, int N, int K,
+                        pb_stream_t stream);
 int pb_fold_gate_t_bf16(const float* W, const float* gate, void* dst, int Bt, int N, int K, pb_stream_t stream);
 /* dst bf16 [F*N][F*K] = diag(W, ..., W) for W bf16 [N][K]: the weight of a row-folded GEMM.  A layer with
  * K <= 32 input channels is run as X'[rows/F][F*K] x dst^T = C'[rows/F][F*N], which is C[rows][N] in memory,
@@ -216,6 +227,13 @@ int pb_stem_conv_fwd(const void* x, int x_dtype, long long xs_b, long long xs_c,
                      void* y, int y_dtype, int B, int Cin, int T, int H, int W, int Cout,
                      int kT, int kH, int kW, int sT, int sH, int sW, int pT, int pH, int pW,
                      int To, int Ho, int Wo, pb_stream_t stream);
+/* inference form: y = act(conv(x) + bias), the stem's eval-mode BatchNorm folded into w / bias by the caller; served by
+ * the tensor-core kernels only (bf16 y, RGB channels-last clip), PB_ERR_UNSUPPORTED otherwise. */
+int pb_stem_conv_fwd_act(const void* x, int x_dtype, long long xs_b, long long xs_c, long long xs_t,
+                     long long xs_h, long long xs_w, float in_div, const float* w, const float* bias,
+                     void* y, int y_dtype, int B, int Cin, int T, int H, int W, int Cout,
+                     int kT, int kH, int kW, int sT, int sH, int sW, int pT, int pH, int pW,
+                     int To, int Ho, int Wo, int act, float slope, pb_stream_t stream);
 int pb_stem_conv_wgrad(const void* x, int x_dtype, long long xs_b, long long xs_c, long long xs_t,
                        long long xs_h, long long xs_w, float in_div, const void* dy, int y_dtype,
                        float* dw, float* dbias, int B, int Cin, int T, int H, int W, int Cout,

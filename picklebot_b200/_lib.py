@@ -29,11 +29,13 @@ SIGNATURES = {
     "pb_stream_dwconv3d_fwd": "pppppi" + "i" * 14 + "p",
     "pb_pw_gemm_simt": "ppllpppppiiliip",
     "pb_pw_gemm_tc": "ppipppp" + "pi" + "iliip",
+    "pb_pw_gemm_tc_act": "ppipppp" + "pi" + "ilii" + "if" + "p",
     "pb_pw_wgrad_simt": "pppppiiliip",
     "pb_pw_wgrad_tc": "pppppppiliip",
     "pb_cast_matrix": "ppiiiip",
     "pb_fold_gate_bf16": "pppiiip",
     "pb_fold_gate_t_bf16": "pppiiip",
+    "pb_fold_scaled_bf16": "ppppiiip",
     "pb_block_diag_bf16": "ppiiip",
     "pb_colstats": "pilipp",
     "pb_bn_finalize": "plppppiffpppppip",
@@ -51,6 +53,7 @@ SIGNATURES = {
     "pb_rowdot": "ppiilipp",
     "pb_scale_add": "pppiilip",
     "pb_stem_conv_fwd": "pi" + "lllll" + "f" + "pppi" + "i" * 18 + "p",
+    "pb_stem_conv_fwd_act": "pi" + "lllll" + "f" + "pppi" + "i" * 18 + "if" + "p",
     "pb_stem_conv_wgrad": "pi" + "lllll" + "f" + "pipp" + "i" * 18 + "p",
     "pb_adamw_step": "pppp" + "ii" + "ffffffff" + "p",
     "pb_ce_loss": "ppppp" + "iif" + "p",

@@ -12,6 +12,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
+import os
+
 import torch
 
 from . import ops
@@ -201,6 +203,64 @@ def bn_forward(z: torch.Tensor, B: int, C: int, gamma, beta, rmean, rvar, nbt, t
                                                  z.device, nbt=nbt if use_batch else None)
     out = ops.bn_act_fwd(z, scale, shift, mask, B, C, act, slope)
     return out, (scale, shift, mean, invstd)
+
+
+# ---------------------------------------------------------------------------------------------
+# inference fast paths (no autograd): the eval-mode BatchNorm that follows a convolution is folded into it --
+# scale into the bf16 weights, shift into a bias that pre-loads the TMEM accumulator, activation in the GEMM / stem
+# epilogue -- so the BN/activation pass over the block's output (one read + one write) and its launch disappear.
+# Only for bf16 activations on the tensor-core kernels; everything else takes the general path.
+# ---------------------------------------------------------------------------------------------
+def eval_fold_ok(x_dtype: torch.dtype, training: bool, rmean) -> bool:
+    return (not training and rmean is not None and not torch.is_grad_enabled() and x_dtype == torch.bfloat16
+            and ops._TC_READY and not ops._FORCE_SIMT and not os.environ.get("PB_NO_EVAL_FOLD"))
+
+
+def pw_fwd_folded(A: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, act: int, slope: float,
+                  gate=None, Bt: int = 1) -> torch.Tensor:
+    """act((A * gate) W^T * scale + shift): conv -> BN(eval) -> act as ONE GEMM."""
+    W = _w2d(w).detach().contiguous()
+    N, K = W.shape
+    rows = A.numel() // K
+    Wb = ops.fold_scaled(W, gate, scale)                          # [Bt or 1][N][K]
+    if gate is None:
+        F = _row_fold(rows, K)
+        if F > 1 and N * F <= 256:
+            Wf = ops.block_diag(Wb.view(N, K), F)
+            return gemm_tc.gemm(A, Wf, N * F, K * F, bias=shift.repeat(F).contiguous(), act=act, slope=slope).view(-1, N)
+        return gemm_tc.gemm(A, Wb.view(N, K), N, K, Bw=1, Bt=1, bias=shift, act=act, slope=slope).view(-1, N)
+    return gemm_tc.gemm(A, Wb, N, K, Bw=Bt, Bt=Bt, bias=shift, act=act, slope=slope).view(-1, N)
+
+
+def bottleneck_eval(x, cfg: BlockCfg, cache: WeightCache, rmean, rvar, w1, wdw, w2, gamma, beta,
+                    se_w1, se_b1, se_w2, se_b2):
+    """Bottleneck3D.forward in eval mode (mobilenet.py:84-93) with the BatchNorm folded into the projection."""
+    x5 = to_ndhwc(x)
+    B, T, H, W, Cin = x5.shape
+    Cexp, Cout = w1.shape[0], w2.shape[0]
+    dt = x5.dtype
+    y1 = pw_fwd(x5.view(-1, Cin), w1, cache, "w1").view(B, T, H, W, Cexp)
+    wdw_tc = cache.get(("wdw", dt), wdw, lambda: ops.dw_weight_tapmajor(wdw, dt))
+    gate = None
+    if cfg.use_se:
+        y2, pooled = ops.dwconv_fwd_pool(y1, wdw_tc, cfg.k, cfg.s, cfg.p)
+        _, gate = ops.se_fc_fwd(pooled, _w2d(se_w1), se_b1.detach(), _w2d(se_w2), se_b2.detach())
+    else:
+        y2 = ops.dwconv_fwd(y1, wdw_tc, cfg.k, cfg.s, cfg.p)
+    _, To, Ho, Wo, _ = y2.shape
+    scale, shift, _, _ = ops.bn_finalize(None, 1, gamma.detach(), beta.detach(), rmean, rvar, False, 0.0, cfg.eps, Cout,
+                                         x5.device)
+    out = pw_fwd_folded(y2.view(-1, Cexp), w2, scale, shift, cfg.act, cfg.slope, gate=gate, Bt=B if gate is not None else 1)
+    return from_ndhwc(out.view(B, To, Ho, Wo, Cout))
+
+
+def stem_eval(x, k, s, p, dt, eps, rmean, rvar, w, bias, gamma, beta):
+    """block1 (Conv3d 3->16 + BatchNorm3d(eval) + Hardswish, mobilenet.py:141-143) as one kernel."""
+    Cout = w.shape[0]
+    scale, shift, _, _ = ops.bn_finalize(None, 1, gamma.detach(), beta.detach(), rmean, rvar, False, 0.0, eps, Cout, x.device)
+    wf = (w.detach().float() * scale.view(Cout, 1, 1, 1, 1)).contiguous()
+    bf = shift if bias is None else torch.addcmul(shift, bias.detach().float(), scale)
+    return from_ndhwc(ops.stem_fwd(x, wf, bf.contiguous(), k, s, p, dt, act=ACT_CODES["hswish"]))
 
 
 # ---------------------------------------------------------------------------------------------

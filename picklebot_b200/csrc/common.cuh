@@ -161,6 +161,24 @@ __device__ __forceinline__ float act_fwd(float u, int act, float slope) {
         default:              return u;
     }
 }
+// activation of a register vector with a RUN-TIME code: one switch around the loop, not one per element
+template <int NV>
+__device__ __forceinline__ void act_fwd_vec(float (&v)[NV], int act, float slope) {
+    switch (act) {
+        case PB_ACT_NONE: break;
+        case PB_ACT_RELU:
+#pragma unroll
+            for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
+            break;
+        case PB_ACT_HSWISH:
+#pragma unroll
+            for (int j = 0; j < NV; ++j) v[j] = v[j] * fminf(fmaxf(v[j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
+            break;
+        default:
+#pragma unroll
+            for (int j = 0; j < NV; ++j) v[j] = act_fwd(v[j], act, slope);
+    }
+}
 __device__ __forceinline__ float act_grad(float u, int act, float slope) {
     switch (act) {
         case PB_ACT_RELU:     return u > 0.f ? 1.f : 0.f;

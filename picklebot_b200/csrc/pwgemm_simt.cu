@@ -187,6 +187,34 @@ __global__ void fold_gate_kernel(const float* __restrict__ W, const float* __res
     *reinterpret_cast<uint4*>(dst + idx * 8) = o;
 }
 
+// Inference: dst[b][n][k] = W[n][k] * gate[b][k] * rowscale[n] -- the squeeze-excite gate (optional) and the scale of
+// the eval-mode BatchNorm that follows the convolution (optional) folded into one bf16 weight matrix per sample.
+__global__ void fold_scaled_kernel(const float* __restrict__ W, const float* __restrict__ gate,
+                                   const float* __restrict__ rowscale, __nv_bfloat16* __restrict__ dst, int N, int K,
+                                   long long total8) {
+    pdl_trigger();
+    pdl_wait();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total8) return;
+    const int K8 = K >> 3;
+    const int k = (int)(idx % K8) << 3;
+    const long long q = idx / K8;
+    const int n = (int)(q % N);
+    const int b = (int)(q / N);
+    const float4* wp = reinterpret_cast<const float4*>(W + (long long)n * K + k);
+    const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+    float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+    if (gate) {
+        const float4* gp = reinterpret_cast<const float4*>(gate + (long long)b * K + k);
+        g0 = __ldg(gp); g1 = __ldg(gp + 1);
+    }
+    const float rs = rowscale ? __ldg(rowscale + n) : 1.f;
+    uint4 o;
+    o.x = pack_bf16x2(w0.x * g0.x * rs, w0.y * g0.y * rs); o.y = pack_bf16x2(w0.z * g0.z * rs, w0.w * g0.w * rs);
+    o.z = pack_bf16x2(w1.x * g1.x * rs, w1.y * g1.y * rs); o.w = pack_bf16x2(w1.z * g1.z * rs, w1.w * g1.w * rs);
+    *reinterpret_cast<uint4*>(dst + idx * 8) = o;
+}
+
 // Transposed twin for the input-gradient GEMM of a squeeze-excite block: dst[b][k][n] = W[n][k] * gate[b][k]
 // (W fp32 [N][K] as stored by the layer, dst bf16 [B][K][N]): the gate scales the ROWS of the transposed weight,
 // i.e. the output columns of  dy2 = dz W  -- folded here so that GEMM needs no per-column epilogue vector.
@@ -294,6 +322,19 @@ extern "C" int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, i
     (void)launch_pdl(fold_gate_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, W, gate,
                      (__nv_bfloat16*)dst, N, K, n);
     PB_CHECK_LAUNCH("fold_gate_kernel");
+    return PB_OK;
+}
+
+extern "C" int pb_fold_scaled_bf16(const float* W, const float* gate, const float* rowscale, void* dst, int Bt, int N,
+                                   int K, pb_stream_t stream) {
+    PB_REQUIRE(W && dst && Bt > 0 && N > 0 && K > 0 && K % 8 == 0, "fold_scaled: bad args (K %% 8 == 0)");
+    PB_REQUIRE(gate || Bt == 1, "fold_scaled: Bt > 1 needs a gate");
+    PB_REQUIRE(((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(gate) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0,
+               "fold_scaled: pointers must be 16-byte aligned");
+    long long n = (long long)Bt * N * (K / 8);
+    (void)launch_pdl(fold_scaled_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, W, gate, rowscale,
+                     (__nv_bfloat16*)dst, N, K, n);
+    PB_CHECK_LAUNCH("fold_scaled_kernel");
     return PB_OK;
 }
 

@@ -55,13 +55,19 @@ struct GemmParams {
     const float* bias;
     const float* colscale;
     const float* coladd;
-    const float* tinit;  // per-sample additive vector [Bt][N] applied by PRE-LOADING the accumulator (see the epilogue warps)
+    const float* tinit;  // additive vector applied by PRE-LOADING the accumulator (see the epilogue warps):
+    int tinit_bstride;   //   tinit[b * tinit_bstride + n]; stride N = per sample, 0 = shared (a bias)
+    int act;             // activation applied to the fp32 accumulators by the plain epilogue (PB_ACT_*)
+    float slope;
     __nv_bfloat16* C;
     double* stats;     // optional BatchNorm statistics of C: [PB_STAT_REPLICAS][2][stat_mod] sums of x and x^2
     int stat_mod;      // real channel count (column c of a row-folded problem is channel c % stat_mod)
 };
 
-template <bool EPI, bool STATS>   // EPI: any of bias / colscale / coladd present; STATS: column sums of C
+// EPI: any of bias / colscale / coladd present; STATS: column sums of C; ACT: activation in the plain epilogue
+// (a template flag so that the training kernels keep their register allocation: with a run-time test the plain
+// kernel lost 12 % on the whole step)
+template <bool EPI, bool STATS, bool ACT = false>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -175,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         auto preload = [&](long long t, int a) {
             const int n_tile = (int)(t % p.n_tiles);
             const int b = (int)((t / p.n_tiles) / p.m_tiles);
-            const float* src = p.tinit + (long long)b * p.N + n_tile * p.block_n;
+            const float* src = p.tinit + (long long)b * p.tinit_bstride + n_tile * p.block_n;
             const int ncols = min(p.block_n, p.N - n_tile * p.block_n);
             for (int sub = 0; sub < p.mt; ++sub) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_cols + sub * p.block_n);
@@ -339,6 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float v[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[g][j]);
+                            if (ACT) act_fwd_vec(v, p.act, p.slope);
                             uint4 o0, o1;
                             o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
                             o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
@@ -425,9 +432,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 using namespace pb;
 using namespace pb::tc;
 
+extern "C" int pb_pw_gemm_tc_act(const void* A, const void* W_bf16, int Bw, const float* bias, const float* colscale,
+                                 const float* coladd, void* C, double* stats, int stat_mod, int Bt, long long R, int K,
+                                 int N, int act, float slope, pb_stream_t stream);
+
 extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const float* bias, const float* colscale,
                              const float* coladd, void* C, double* stats, int stat_mod, int Bt, long long R, int K,
                              int N, pb_stream_t stream) {
+    return pb_pw_gemm_tc_act(A, W_bf16, Bw, bias, colscale, coladd, C, stats, stat_mod, Bt, R, K, N, PB_ACT_NONE, 0.f, stream);
+}
+
+// act != PB_ACT_NONE: C = act(A W^T + bias) -- the inference form of conv -> BatchNorm(eval) -> activation once the
+// caller has folded the BatchNorm scale into W and its shift into bias (blocks.py bottleneck_eval).  Only with a
+// shared bias or a per-sample coladd alone (both pre-load the accumulator) or no vector at all.
+extern "C" int pb_pw_gemm_tc_act(const void* A, const void* W_bf16, int Bw, const float* bias, const float* colscale,
+                                 const float* coladd, void* C, double* stats, int stat_mod, int Bt, long long R, int K,
+                                 int N, int act, float slope, pb_stream_t stream) {
     PB_REQUIRE(A && W_bf16 && C, "pw_gemm_tc: null pointer");
     PB_REQUIRE(Bt > 0 && R > 0 && K > 0 && N > 0, "pw_gemm_tc: empty problem");
     PB_REQUIRE(K % 8 == 0 && N % 8 == 0, "pw_gemm_tc: K=%d and N=%d must be multiples of 8", K, N);
@@ -465,8 +485,14 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
     // A per-sample additive vector alone does not need the fp32 epilogue: the accumulator is pre-loaded with it
     // (tcgen05.st by the epilogue warps) and the bf16 panel path stores the result.  PB_GEMM_NO_TINIT=1 keeps the
     // old route for A/B tests.
-    p.tinit = nullptr;
-    if (coladd && !bias && !colscale && !stats && !getenv("PB_GEMM_NO_TINIT")) { p.tinit = coladd; coladd = nullptr; }
+    p.tinit = nullptr; p.tinit_bstride = 0;
+    if (!stats && !colscale && !getenv("PB_GEMM_NO_TINIT")) {
+        if (coladd && !bias) { p.tinit = coladd; p.tinit_bstride = N; coladd = nullptr; }
+        else if (bias && !coladd) { p.tinit = bias; p.tinit_bstride = 0; bias = nullptr; }
+    }
+    p.act = act; p.slope = slope;
+    PB_REQUIRE(act == PB_ACT_NONE || (!bias && !colscale && !coladd && !stats),
+               "pw_gemm_tc: an activation needs the plain epilogue (no statistics, at most one additive vector)");
     p.bias = bias; p.colscale = colscale; p.coladd = coladd; p.C = (__nv_bfloat16*)C;
     p.stats = stats; p.stat_mod = stat_mod;
     if (stats) {
@@ -489,8 +515,9 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
         uint32_t box[3] = {(uint32_t)BK, (uint32_t)p.block_n, 1};
         if (int e = make_tmap_bf16(&tmW, W_bf16, 3, dims, str, box, BK * 2)) return e;
     }
-    static unsigned long long attr_done[3] = {0, 0, 0};
+    static unsigned long long attr_done[4] = {0, 0, 0, 0};
     cudaError_t attr_err = ensure_dyn_smem(gemm_tc_kernel<false, false>, 226 * 1024, &attr_done[0]);
+    if (attr_err == cudaSuccess) attr_err = ensure_dyn_smem(gemm_tc_kernel<false, false, true>, 226 * 1024, &attr_done[3]);
     if (attr_err == cudaSuccess) attr_err = ensure_dyn_smem(gemm_tc_kernel<true, false>, 226 * 1024, &attr_done[1]);
     if (attr_err == cudaSuccess) attr_err = ensure_dyn_smem(gemm_tc_kernel<false, true>, 226 * 1024, &attr_done[2]);
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(gemm_tc_kernel)");
@@ -503,6 +530,9 @@ extern "C" int pb_pw_gemm_tc(const void* A, const void* W_bf16, int Bw, const fl
                            p));
     else if (stats)
         PB_CUDA(launch_pdl(gemm_tc_kernel<false, true>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW,
+                           p));
+    else if (p.act != PB_ACT_NONE)
+        PB_CUDA(launch_pdl(gemm_tc_kernel<false, false, true>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW,
                            p));
     else
         PB_CUDA(launch_pdl(gemm_tc_kernel<false, false>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW,

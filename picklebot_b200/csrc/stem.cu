@@ -193,6 +193,7 @@ static StemTc stem_tc_dims(const StemDims& d) {
     t.P = (long long)d.B * d.To * d.Ho * d.Wo;
     t.steps = (t.P + 255) / 256;
     t.inv_scale = 1.0f / d.in_scale;
+    t.act = PB_ACT_NONE; t.slope = 0.f;
     return t;
 }
 
@@ -223,6 +224,24 @@ using namespace pb;
             else { set_error("stem: bad x dtype"); return PB_ERR_BAD_ARG; }                         \
         } else { set_error("stem: bad y dtype"); return PB_ERR_BAD_ARG; }                           \
     } while (0)
+
+// Inference form: y = act(conv(x) + bias) with the eval-mode BatchNorm of the stem already folded into w / bias by the
+// caller (blocks.py stem_eval).  tcgen05 kernels only (bf16 output); PB_ERR_UNSUPPORTED otherwise.
+extern "C" int pb_stem_conv_fwd_act(const void* x, int x_dtype, STEM_ARGS, const float* w, const float* bias, void* y,
+                                    int y_dtype, STEM_DIMS, int act, float slope, pb_stream_t stream) {
+    STEM_PACK;
+    if (int e = stem_check(d)) return e;
+    PB_REQUIRE(x && w && y, "stem_conv_fwd_act: null pointer");
+    StemTc t = stem_tc_dims(d);
+    t.act = act; t.slope = slope;
+    if (stem_tc_eligible(d, y_dtype) && stem_tc_fwd(x, x_dtype, w, bias, y, kT, t, (cudaStream_t)stream)) {
+        PB_CHECK_LAUNCH("stem_tc_fwd_kernel");
+        count_path(PB_PATH_STEM_TC);
+        return PB_OK;
+    }
+    set_error("stem_conv_fwd_act: shape / dtype not covered by the tensor-core stem kernels");
+    return PB_ERR_UNSUPPORTED;
+}
 
 extern "C" int pb_stem_conv_fwd(const void* x, int x_dtype, STEM_ARGS, const float* w, const float* bias, void* y,
                                 int y_dtype, STEM_DIMS, pb_stream_t stream) {

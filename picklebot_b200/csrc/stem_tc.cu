@@ -229,15 +229,15 @@ stem_tc_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ w, const 
             tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(pst * 32 + (warp >> 2) * 16), r);
             tmem_ld_wait();
             if (p < d.P) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bv[j];
+                act_fwd_vec(v, d.act, d.slope);
                 uint4 o0, o1;
-                o0.x = pack_bf16x2(__uint_as_float(r[0]) + bv[0], __uint_as_float(r[1]) + bv[1]);
-                o0.y = pack_bf16x2(__uint_as_float(r[2]) + bv[2], __uint_as_float(r[3]) + bv[3]);
-                o0.z = pack_bf16x2(__uint_as_float(r[4]) + bv[4], __uint_as_float(r[5]) + bv[5]);
-                o0.w = pack_bf16x2(__uint_as_float(r[6]) + bv[6], __uint_as_float(r[7]) + bv[7]);
-                o1.x = pack_bf16x2(__uint_as_float(r[8]) + bv[8], __uint_as_float(r[9]) + bv[9]);
-                o1.y = pack_bf16x2(__uint_as_float(r[10]) + bv[10], __uint_as_float(r[11]) + bv[11]);
-                o1.z = pack_bf16x2(__uint_as_float(r[12]) + bv[12], __uint_as_float(r[13]) + bv[13]);
-                o1.w = pack_bf16x2(__uint_as_float(r[14]) + bv[14], __uint_as_float(r[15]) + bv[15]);
+                o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+                o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+                o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+                o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
                 uint4* dst = reinterpret_cast<uint4*>(y + p * 16);
                 dst[0] = o0; dst[1] = o1;
             }
@@ -554,15 +554,15 @@ stem_tma_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const float* __rest
                 const int ho = c.hg * g.RT + qr;
                 if (qr < g.RT && ho < d.Ho) {
                     const long long p = (((long long)c.b * d.To + c.to) * d.Ho + ho) * d.Wo + qw;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(rg[j]), inv, bv[j]);
+                    act_fwd_vec(v, d.act, d.slope);
                     uint4 o0, o1;
-                    o0.x = pack_bf16x2(fmaf(__uint_as_float(rg[0]), inv, bv[0]), fmaf(__uint_as_float(rg[1]), inv, bv[1]));
-                    o0.y = pack_bf16x2(fmaf(__uint_as_float(rg[2]), inv, bv[2]), fmaf(__uint_as_float(rg[3]), inv, bv[3]));
-                    o0.z = pack_bf16x2(fmaf(__uint_as_float(rg[4]), inv, bv[4]), fmaf(__uint_as_float(rg[5]), inv, bv[5]));
-                    o0.w = pack_bf16x2(fmaf(__uint_as_float(rg[6]), inv, bv[6]), fmaf(__uint_as_float(rg[7]), inv, bv[7]));
-                    o1.x = pack_bf16x2(fmaf(__uint_as_float(rg[8]), inv, bv[8]), fmaf(__uint_as_float(rg[9]), inv, bv[9]));
-                    o1.y = pack_bf16x2(fmaf(__uint_as_float(rg[10]), inv, bv[10]), fmaf(__uint_as_float(rg[11]), inv, bv[11]));
-                    o1.z = pack_bf16x2(fmaf(__uint_as_float(rg[12]), inv, bv[12]), fmaf(__uint_as_float(rg[13]), inv, bv[13]));
-                    o1.w = pack_bf16x2(fmaf(__uint_as_float(rg[14]), inv, bv[14]), fmaf(__uint_as_float(rg[15]), inv, bv[15]));
+                    o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+                    o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+                    o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+                    o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
                     uint4* dst = reinterpret_cast<uint4*>(y + p * 16);
                     dst[0] = o0; dst[1] = o1;
                 }

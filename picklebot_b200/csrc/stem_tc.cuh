@@ -11,6 +11,8 @@ struct StemTc {
     long long P;                      // output pixels
     long long steps;                  // 256-pixel steps
     float inv_scale;                  // uint8 clips: 1 / in_scale (train.py:106's /255)
+    int act;                          // activation applied by the forward epilogue (PB_ACT_*; inference with BN folded)
+    float slope;
 };
 
 // Return true if they launched; false = not covered (caller uses the direct kernels).

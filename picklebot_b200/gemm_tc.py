@@ -15,7 +15,7 @@ _WGRAD_READY = os.environ.get("PB_TC_WGRAD", "1") != "0"
 
 
 def gemm(A: torch.Tensor, Wb: torch.Tensor, N: int, K: int, Bw: int = 1, Bt: int = 1, bias=None, colscale=None,
-         coladd=None, stat_mod: int = 0):
+         coladd=None, stat_mod: int = 0, act: int = 0, slope: float = 0.0):
     """A bf16 [Bt][R][K] (contiguous), Wb bf16 [Bw][N][K] -> bf16 [Bt*R][N];
     C = (A W^T + bias) * colscale[b] + coladd[b].
     stat_mod > 0: also returns the BatchNorm sums of C ([STAT_REPLICAS][2][stat_mod] fp64, channel = column % stat_mod),
@@ -26,6 +26,11 @@ def gemm(A: torch.Tensor, Wb: torch.Tensor, N: int, K: int, Bw: int = 1, Bt: int
     R = rows // Bt
     C = torch.empty((rows, N), dtype=torch.bfloat16, device=A.device)
     sums = torch.empty((_lib.STAT_REPLICAS, 2, stat_mod), dtype=torch.float64, device=A.device) if stat_mod else None
+    if act:     # C = act(A W^T + bias): inference with the eval-mode BatchNorm folded into Wb / bias
+        call("pb_pw_gemm_tc_act", A.data_ptr(), Wb.data_ptr(), Bw, _p(bias), _p(colscale), _p(coladd), C.data_ptr(),
+             _p(sums), stat_mod, Bt, R, K, N, act, float(slope), _st(),
+             nbytes=(A.numel() + C.numel() + Wb.numel()) * 2, wbytes=C.numel() * 2)
+        return (C, sums) if stat_mod else C
     call("pb_pw_gemm_tc", A.data_ptr(), Wb.data_ptr(), Bw, _p(bias), _p(colscale), _p(coladd), C.data_ptr(),
          _p(sums), stat_mod, Bt, R, K, N, _st(), nbytes=(A.numel() + C.numel() + Wb.numel()) * 2, wbytes=C.numel() * 2)
     return (C, sums) if stat_mod else C

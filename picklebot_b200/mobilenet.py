@@ -137,6 +137,10 @@ class Bottleneck3D(nn.Module):
         if mask is None and self.dropout.training and cfg.p_drop > 0:
             mask = blocks.draw_dropout3d_mask(x.shape[0], bn.num_features, cfg.p_drop, dt, x.device)
         se = self.squeeze_excite.params() if self.squeeze_excite is not None else (None, None, None, None)
+        if mask is None and blocks.eval_fold_ok(dt, bn.training, bn.running_mean):
+            return blocks.bottleneck_eval(x, cfg, self._cache, bn.running_mean, bn.running_var,
+                                          self.pointwise_conv1.weight, self.depthwise_conv.weight,
+                                          self.pointwise_conv2.weight, bn.weight, bn.bias, *se)
         return BottleneckFn.apply(x, cfg, self._cache, bn.training, mask,
                                   bn.running_mean, bn.running_var, bn.num_batches_tracked,
                                   self.pointwise_conv1.weight, self.depthwise_conv.weight,
@@ -151,6 +155,10 @@ class _MobileNet3DBase(nn.Module):
     def _stem(self, x, dt):
         conv, bn = self.block1[0], self.block1[1]
         eps, mom, rm, rv, nbt = _bn_args(bn)
+        if (blocks.eval_fold_ok(dt, bn.training, rm) and x.dtype == torch.uint8 and x.stride(1) == 1
+                and tuple(conv.kernel_size)[1:] == (3, 3)):
+            return blocks.stem_eval(x, tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding), dt, eps, rm, rv,
+                                    conv.weight, conv.bias, bn.weight, bn.bias)
         return StemFn.apply(x, tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding), dt, bn.training,
                             eps, mom, rm, rv, nbt, conv.weight, conv.bias, bn.weight, bn.bias)
 

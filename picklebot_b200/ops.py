@@ -114,6 +114,17 @@ def fold_gate(W: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def fold_scaled(W: torch.Tensor, gate: Optional[torch.Tensor], rowscale: Optional[torch.Tensor]) -> torch.Tensor:
+    """bf16 [B][N][K] = W[n][k] * gate[b][k] * rowscale[n] (either factor optional; B = 1 without a gate): inference
+    weights with the squeeze-excite gate and the following eval-mode BatchNorm's scale folded in."""
+    _f32(W, "fold_scaled.W"); _f32(gate, "fold_scaled.gate"); _f32(rowscale, "fold_scaled.rowscale")
+    N, K = W.shape[0], W.shape[1]
+    B = gate.shape[0] if gate is not None else 1
+    dst = torch.empty((B, N, K), dtype=torch.bfloat16, device=W.device)
+    call("pb_fold_scaled_bf16", W.data_ptr(), _p(gate), _p(rowscale), dst.data_ptr(), B, N, K, _st())
+    return dst
+
+
 def fold_gate_t(W: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
     """bf16 [B][K][N] = W[n][k] * gate[b][k]: the per-sample weights of the input-gradient GEMM  dy2 = (dz W) * gate."""
     _f32(W, "fold_gate_t.W"); _f32(gate, "fold_gate_t.gate")
@@ -388,12 +399,18 @@ def _stem_args(x: torch.Tensor, k, s, p, Cout: int):
     return (sb, sc, st, sh, sw), dims, (B, To, Ho, Wo, Cout)
 
 
-def stem_fwd(x: torch.Tensor, w: torch.Tensor, bias, k, s, p, out_dtype: torch.dtype) -> torch.Tensor:
-    """x: logical (B,Cin,T,H,W) with ANY strides, dtype uint8 (divided by 255) / fp32 / bf16."""
+def stem_fwd(x: torch.Tensor, w: torch.Tensor, bias, k, s, p, out_dtype: torch.dtype, act: int = 0,
+             slope: float = 0.0) -> torch.Tensor:
+    """x: logical (B,Cin,T,H,W) with ANY strides, dtype uint8 (divided by 255) / fp32 / bf16.
+    act != 0: y = act(conv + bias) (inference with the BatchNorm folded into w / bias; tensor-core kernels only)."""
     if not x.is_cuda:
         raise RuntimeError("stem_fwd: picklebot_b200 kernels need CUDA tensors (there is no CPU fallback)")
     strides, dims, oshape = _stem_args(x, k, s, p, w.shape[0])
     y = torch.empty(oshape, dtype=out_dtype, device=x.device)
+    if act:
+        call("pb_stem_conv_fwd_act", x.data_ptr(), _dt(x), *strides, 255.0, w.data_ptr(), _p(bias), y.data_ptr(), _dt(y),
+             *dims, act, float(slope), _st(), nbytes=x.numel() * x.element_size() + y.numel() * y.element_size())
+        return y
     call("pb_stem_conv_fwd", x.data_ptr(), _dt(x), *strides, 255.0, w.data_ptr(), _p(bias), y.data_ptr(), _dt(y),
          *dims, _st(), nbytes=x.numel() * x.element_size() + y.numel() * y.element_size())
     return y

@@ -74,6 +74,30 @@ def test_gemm_tc_se_input_gradient(case, monkeypatch):
     assert rel_err(dy2.float(), alt.float()) < 3e-3
 
 
+@pytest.mark.parametrize("case", [(1, 5000, 96, 24, "hswish", False), (4, 800, 672, 112, "hswish", True),
+                                  (1, 3000, 64, 24, "relu", False), (64, 49, 960, 160, "hswish", True),
+                                  (1, 777, 240, 80, "none", False), (3, 130, 72, 40, "relu", True)])
+def test_gemm_tc_folded_bn_act(case):
+    """Inference form of conv -> BatchNorm(eval) -> activation: scale (and the squeeze-excite gate) folded into bf16
+    weights by pb_fold_scaled_bf16, shift pre-loaded into the accumulator, activation in the epilogue
+    (pb_pw_gemm_tc_act) -- against the unfused fp32 math."""
+    import torch.nn.functional as F
+    from picklebot_b200 import gemm_tc, ops
+    Bt, R, K, N, act, gated = case
+    A = rnd(Bt * R, K, seed=1).bfloat16()
+    W = rnd(N, K, seed=2, scale=0.3)
+    gate = (rnd(Bt, K, seed=3).abs() + 0.1) if gated else None
+    scale, shift = rnd(N, seed=4).abs() + 0.5, rnd(N, seed=5)
+    Wb = ops.fold_scaled(W, gate, scale)
+    full = W[None] * scale[None, :, None] * (gate[:, None, :] if gated else 1.0)
+    assert Wb.shape == ((Bt if gated else 1), N, K) and rel_err(Wb.float(), full) < 4e-3
+    C = gemm_tc.gemm(A, Wb if gated else Wb.view(N, K), N, K, Bw=Bt if gated else 1, Bt=Bt if gated else 1,
+                     bias=shift, act=ops.ACT_CODES[act])
+    pre = torch.einsum("brk,bnk->brn", A.float().view(Bt, R, K), Wb.float().expand(Bt, N, K)).reshape(-1, N) + shift
+    ref = {"hswish": F.hardswish, "relu": F.relu, "none": lambda t: t}[act](pre)
+    assert rel_err(C.float(), ref) < 6e-3
+
+
 @pytest.mark.parametrize("case", [(4000, 16, 16, 4), (4000, 16, 64, 4), (1002, 24, 72, 2), (6000, 32, 96, 2)])
 def test_gemm_tc_row_folded(case):
     """K <= 32 layers run as X'[rows/F][F*K] against diag(W, ..., W) (pb_block_diag_bf16): same bytes out."""

@@ -88,6 +88,38 @@ def test_eval_bf16_autocast_and_uint8_input(model):
     assert torch.equal(mine_u8.argmax(1).cpu(), truth.argmax(1))
 
 
+@pytest.mark.parametrize("model", ["MobileNetLarge3D", "MobileNetSmall3D"])
+def test_eval_bn_folding_matches_unfolded(model, monkeypatch):
+    """Inference fast path (blocks.bottleneck_eval / stem_eval): eval-mode BatchNorm folded into the projection GEMM
+    and the stem, activation in their epilogues.  Same logits as the general path to bf16 accuracy, as close to the
+    fp32 truth, and the BN passes are gone (no pb_bn_act_fwd launches from the stem and the bottlenecks)."""
+    from picklebot_b200 import _lib
+    g = golden(model)
+    m = build(model, g["num_classes"]).eval()
+    B, T, H, W = g["full_shape"]
+    clips = synth.synthetic_clips_u8(B, T, H, W).cuda().permute(0, 4, 1, 2, 3)
+    truth = g["eval_full_logits"]
+    prof = _lib.KernelProfiler()
+    with torch.no_grad():
+        _lib.PROFILER = prof
+        try:
+            folded = m(clips)
+        finally:
+            _lib.PROFILER = None
+        monkeypatch.setenv("PB_NO_EVAL_FOLD", "1")
+        plain = m(clips)
+    torch.cuda.synchronize()
+    names = [r[0] for r in prof.records]
+    assert names.count("pb_bn_act_fwd") <= 2, names.count("pb_bn_act_fwd")       # the tail only
+    assert "pb_pw_gemm_tc_act" in names and "pb_stem_conv_fwd_act" in names
+    e_f, e_p = rel_err(folded, truth), rel_err(plain, truth)
+    print(f"\n{model}: eval logits vs fp32 truth: folded {e_f:.2e}, unfolded {e_p:.2e}; "
+          f"folded vs unfolded {rel_err(folded, plain):.2e}")
+    assert e_f < max(1e-2, 1.5 * e_p)
+    assert rel_err(folded, plain) < 2e-2
+    assert torch.equal(folded.argmax(1).cpu(), truth.argmax(1))
+
+
 def _train_step_ours(model, m, x, labels, masks):
     m.train()
     m.zero_grad(set_to_none=True)
