@@ -49,6 +49,7 @@ struct GemmParams {
     int Bt, K, N, Bw;
     long long R;
     int block_n, n_tiles, m_tiles, k_chunks, stages, mt;
+    int n_res;         // N > 256 with shared weights: a CTA keeps ONE n-tile for its lifetime (weights resident) and strides over row tiles
     int w_resident;    // the whole weight matrix stays in shared memory for the CTA's lifetime (see pb_pw_gemm_tc)
     int bk;            // K elements per chunk = swizzle span / 2: 64 (128B), 32 (64B) or 16 (32B rows) for tiny K
     long long total_tiles;
@@ -63,6 +64,25 @@ struct GemmParams {
     double* stats;     // optional BatchNorm statistics of C: [PB_STAT_REPLICAS][2][stat_mod] sums of x and x^2
     int stat_mod;      // real channel count (column c of a row-folded problem is channel c % stat_mod)
 };
+
+// t = blockIdx.x + i * gridDim.x is the CTA's i-th work item.  Default: item t is tile (t % n_tiles, t / n_tiles).
+// n_res: the CTA owns n-tile blockIdx.x % n_tiles and walks the row tiles with the stride of its group, so the
+// 57-92 KB weight tile of the 112->672 / 160->960 layers is fetched once per CTA instead of once per row tile
+// (it was two thirds of the bytes TMA moved for those layers).
+__device__ __forceinline__ bool tile_coords(const GemmParams& p, long long t, int& n_tile, long long& mtile) {
+    if (!p.n_res) {
+        if (t >= p.total_tiles) return false;
+        n_tile = (int)(t % p.n_tiles);
+        mtile = t / p.n_tiles;
+        return true;
+    }
+    const long long i = t / gridDim.x;
+    n_tile = (int)(blockIdx.x % p.n_tiles);
+    const int rank = (int)(blockIdx.x / p.n_tiles);
+    const int G = ((int)gridDim.x - n_tile - 1) / p.n_tiles + 1;
+    mtile = rank + i * G;
+    return mtile < (long long)p.Bt * p.m_tiles;
+}
 
 // EPI: any of bias / colscale / coladd present; STATS: column sums of C; ACT: activation in the plain epilogue
 // (a template flag so that the training kernels keep their register allocation: with a run-time test the plain
@@ -109,12 +129,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int s = 0; uint32_t ph = 0;
             if (p.w_resident) {                 // one weight tile for every row tile: fetch it once
                 mbar_expect_tx(&wres_bar, (uint32_t)wres_bytes);
+                const int n0 = p.n_res ? (int)(blockIdx.x % p.n_tiles) * p.block_n : 0;
                 for (int kc = 0; kc < p.k_chunks; ++kc)
-                    tma_load_3d(wres + (size_t)kc * w_bytes, &tmW, &wres_bar, kc * BK, 0, 0);
+                    tma_load_3d(wres + (size_t)kc * w_bytes, &tmW, &wres_bar, kc * BK, n0, 0);
             }
-            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const int n_tile = (int)(t % p.n_tiles);
-                const long long mtile = t / p.n_tiles;
+            int n_tile; long long mtile;
+            for (long long t = blockIdx.x; tile_coords(p, t, n_tile, mtile); t += gridDim.x) {
                 const int b = (int)(mtile / p.m_tiles), m_tile = (int)(mtile % p.m_tiles);
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
@@ -137,7 +157,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&wres_bar, 0);
                 tc_fence_after();
             }
-            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            int n_tile_u; long long mtile_u;
+            for (long long t = blockIdx.x; tile_coords(p, t, n_tile_u, mtile_u); t += gridDim.x, ++it) {
                 const int a = (int)(it & 1);
                 const uint32_t aph = (uint32_t)((it >> 1) & 1);
                 // tinit: the epilogue group pre-loads the accumulator and arrives once more up front, so the n-th use
@@ -179,8 +200,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // tinit: write the per-sample additive vector of tile t into every row of accumulator stage `a` (each warp its
         // 32 TMEM lanes), so that the MMAs accumulate on top of it and the plain bf16 epilogue below serves the call
         auto preload = [&](long long t, int a) {
-            const int n_tile = (int)(t % p.n_tiles);
-            const int b = (int)((t / p.n_tiles) / p.m_tiles);
+            int n_tile; long long mt_;
+            (void)tile_coords(p, t, n_tile, mt_);
+            const int b = (int)(mt_ / p.m_tiles);
             const float* src = p.tinit + (long long)b * p.tinit_bstride + n_tile * p.block_n;
             const int ncols = min(p.block_n, p.N - n_tile * p.block_n);
             for (int sub = 0; sub < p.mt; ++sub) {
@@ -213,19 +235,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         if (p.tinit) {
             const long long t0 = (long long)blockIdx.x + (long long)group * gridDim.x;
-            if (t0 < p.total_tiles) {
+            int nt_; long long mt_;
+            if (tile_coords(p, t0, nt_, mt_)) {
                 preload(t0, group);
                 tc_fence_before();
                 mbar_arrive(&tempty_bar[group]);
             }
         }
         long long it = 0;
-        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        int n_tile; long long mtile;
+        for (long long t = blockIdx.x; tile_coords(p, t, n_tile, mtile); t += gridDim.x, ++it) {
             const int a = (int)(it & 1);
             if (a != group) continue;
             const uint32_t aph = (uint32_t)((it >> 1) & 1);
-            const int n_tile = (int)(t % p.n_tiles);
-            const long long mtile = t / p.n_tiles;
             const int b = (int)(mtile / p.m_tiles), m_tile = (int)(mtile % p.m_tiles);
             const int n_base = n_tile * p.block_n;
             const float* cs = p.colscale ? p.colscale + (long long)b * p.N : nullptr;
@@ -388,7 +410,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                 }
             }
-            if (p.tinit && t + 2LL * gridDim.x < p.total_tiles) preload(t + 2LL * gridDim.x, a);
+            if (p.tinit) {
+                int nt_; long long mt_;
+                if (tile_coords(p, t + 2LL * gridDim.x, nt_, mt_)) preload(t + 2LL * gridDim.x, a);
+            }
             tc_fence_before();
             mbar_arrive(&tempty_bar[a]);
         }
@@ -478,7 +503,12 @@ extern "C" int pb_pw_gemm_tc_act(const void* A, const void* W_bf16, int Bw, cons
     // resident instead of re-fetching block_n TMA rows per row tile (for 40 -> 240 channels that was two thirds of
     // all box rows the TMA unit processed).
     const int wres_bytes = p.k_chunks * p.block_n * BK * 2;
-    p.w_resident = (Bw == 1 && p.n_tiles == 1 && wres_bytes <= 64 * 1024) ? 1 : 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    p.n_res = (Bw == 1 && p.n_tiles > 1 && wres_bytes <= 96 * 1024 && (long long)Bt * p.m_tiles >= sms &&
+               !getenv("PB_GEMM_NO_NRES")) ? 1 : 0;
+    p.w_resident = ((Bw == 1 && p.n_tiles == 1 && wres_bytes <= 64 * 1024) || p.n_res) ? 1 : 0;
     const int stage_bytes = p.w_resident ? p.mt * BM * BK * 2 : (p.mt * BM + p.block_n) * BK * 2;
     p.stages = std::min(MAX_STAGES, (RING_BYTES - (p.w_resident ? wres_bytes : 0)) / stage_bytes);
     PB_REQUIRE(p.stages >= 2, "pw_gemm_tc: internal tiling error");
@@ -521,9 +551,6 @@ extern "C" int pb_pw_gemm_tc_act(const void* A, const void* W_bf16, int Bw, cons
     if (attr_err == cudaSuccess) attr_err = ensure_dyn_smem(gemm_tc_kernel<true, false>, 226 * 1024, &attr_done[1]);
     if (attr_err == cudaSuccess) attr_err = ensure_dyn_smem(gemm_tc_kernel<false, true>, 226 * 1024, &attr_done[2]);
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(gemm_tc_kernel)");
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int grid = (int)std::min<long long>(p.total_tiles, sms);
     if (bias || colscale || coladd)
         PB_CUDA(launch_pdl(gemm_tc_kernel<true, false>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, tmA, tmW,

@@ -15,7 +15,9 @@ def rnd(*shape, seed=0, scale=1.0):
 # (Bt, R, K, N): pointwise layers of the three models, ragged row counts, K tails, N > 256
 CASES = [(1, 128, 64, 16), (1, 1000, 16, 16), (1, 5000, 16, 64), (1, 777, 24, 72), (2, 931, 960, 160),
          (3, 200, 672, 112), (1, 3000, 160, 960), (1, 1234, 112, 672), (4, 37, 72, 40), (1, 4096, 184, 80),
-         (2, 300, 80, 184), (1, 50000, 40, 240), (1, 129, 8, 8), (64, 735, 960, 160)]
+         (2, 300, 80, 184), (1, 50000, 40, 240), (1, 129, 8, 8), (64, 735, 960, 160),
+         # enough row tiles for the n-tile-resident schedule (a CTA keeps one of the 2-4 column tiles)
+         (1, 40000, 160, 960), (1, 30011, 112, 672), (3, 9000, 80, 480)]
 
 
 @pytest.mark.parametrize("case", CASES)
