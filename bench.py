@@ -451,6 +451,11 @@ def main():
         return logits
 
     def micro_step(x_u8, y, sync_grads, eager=False, first=True):
+        if _lib.PROFILER is not None:
+            # instrumented pass: park the GPU for ~15 ms first, so that every launch of this micro-batch is already
+            # queued when the GPU gets to it -- otherwise the event pairs also time the host's ~10 us between two
+            # ctypes calls whenever the GPU has caught up (it inflated the short kernels by 5-15 %, box-dependent)
+            torch.cuda._sleep(30_000_000)
         if mode == "stream":
             return stream_clip(x_u8, eager)
         if mode == "infer":

@@ -398,7 +398,7 @@ bn_bwd_bulk_kernel(const void* __restrict__ dout, const __nv_bfloat16* __restric
     pdl_trigger();
     const uint32_t raw = tc::smem_u32(bnb_smem);
     const uint32_t ring = (raw + 127u) & ~127u;
-    float* sm_fold = reinterpret_cast<float*>(bnb_smem + (ring - raw) + p.stages * p.stage_pitch);   // MODE 0 only
+    float* sm_fold = reinterpret_cast<float*>(bnb_smem + (ring - raw));   // MODE 0: the fold scratch reuses the drained ring
     bnb_init(cx);
     pdl_wait();
     if (threadIdx.x >= BNB_CONSUMERS) {
@@ -454,6 +454,7 @@ bn_bwd_bulk_kernel(const void* __restrict__ dout, const __nv_bfloat16* __restric
         if (++st == p.stages) { st = 0; ph ^= 1u; }
     }
     if (MODE == 0) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // every consumer is done with the ring: it becomes the scratch
         bnb_fold_rows<16>(s, L.G, L.RPI, L.rr, sm_fold);
         if (L.active && L.rr == 0) {
             double* dst = sums + (size_t)(blockIdx.x % PB_STAT_REPLICAS) * 2 * p.C;
@@ -523,11 +524,10 @@ static inline bool bnb_plan(long long M, long long R, int C, int tensors, const 
     if (RPI < 1 || M < 4LL * RPI) return false;
     // ~16 KB of rows per tensor and stage, at least 4 rows per thread and chunk (a chunk costs a barrier round trip:
     // with 2 rows per thread the 960-channel layers ran at 1.6 TB/s)
-    // measured with tools/bn_bench.py (sum over MobileNetLarge3D's 13 BN shapes, L2 flushed): the reduction (two
-    // tensors + 16 KB of fold scratch) is best with 8 KB chunks x 4 stages (613 us; 16 KB x 3 does not fit for narrow
-    // layers: 678 us; register kernel 718 us), the elementwise passes with 16 KB chunks (fwd 468 / apply 612 us
-    // against 500 / 791 us for the register kernels)
-    const int chunk_kb = fold_scratch ? 8 : 16, min_rows = fold_scratch ? 2 : 4;
+    // measured with tools/bn_bench.py (sum over MobileNetLarge3D's 13 BN shapes, L2 flushed): 16 KB chunks, three stages
+    // for two tensors / four for one (fwd 466, reduce 571, apply 616 us against 500 / 718 / 791 us for the register
+    // kernels; 8 KB x 4 stages: 498 / 613 / 623 us).  The reduction's 16 KB fold scratch reuses the drained ring.
+    const int chunk_kb = 16, min_rows = 4;
     int rc = std::max(min_rows * RPI, chunk_kb * 1024 / (C * 2));
     rc = std::max(RPI, rc / RPI * RPI);
     while ((long long)rc * C * 2 > (chunk_kb + 4) * 1024 && rc > RPI) rc -= RPI;
@@ -535,12 +535,12 @@ static inline bool bnb_plan(long long M, long long R, int C, int tensors, const 
     b->nchunks = (unsigned)((M + rc - 1) / rc);
     b->tensor_pitch = ((unsigned)rc * C * 2 + 127u) & ~127u;
     b->stage_pitch = b->tensor_pitch * tensors;
-    b->stages = (tensors == 2 && !fold_scratch) ? 3 : BNB_STAGES;
+    b->stages = tensors == 2 ? 3 : BNB_STAGES;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     *grid = (int)std::min<long long>(b->nchunks, 2LL * sms);
-    *smem = 128 + (size_t)b->stages * b->stage_pitch + (fold_scratch ? 16 * 256 * sizeof(float) : 0);
+    *smem = 128 + std::max((size_t)b->stages * b->stage_pitch, fold_scratch ? 16 * 256 * sizeof(float) : (size_t)0);
     return *smem <= 112 * 1024;
 }
 

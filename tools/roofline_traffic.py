@@ -12,7 +12,10 @@ FAMILIES = [("gemm_tc_kernel", "pb_pw_gemm_tc"), ("wgrad_tc_kernel", "pb_pw_wgra
             ("dw_fwd3d_tma_kernel", "pb_dwconv3d_fwd (kT,3,3)"), ("dw_dgrad_s2_tma_kernel", "pb_dwconv3d_dgrad (stride 2)"),
             ("dw_wgrad_tma_kernel", "pb_dwconv3d_wgrad"), ("bn_act_fwd_kernel", "pb_bn_act_fwd"),
             ("bn_bwd_reduce_kernel", "pb_bn_act_bwd_reduce"), ("bn_bwd_apply_kernel", "pb_bn_act_bwd_apply"),
+            ("bn_bwd_bulk_kernel", "pb_bn_act_bwd_reduce + pb_bn_act_bwd_apply (bulk ring)"),
+            ("bn_act_fwd_bulk_kernel", "pb_bn_act_fwd (bulk ring)"),
             ("stem_tc_fwd_kernel", "pb_stem_conv_fwd"), ("stem_tc_wgrad_kernel", "pb_stem_conv_wgrad"),
+            ("stem_tma_fwd_kernel", "pb_stem_conv_fwd (TMA)"), ("stem_tma_wgrad_kernel", "pb_stem_conv_wgrad (TMA)"),
             ("colreduce_kernel", "pb_pool_fwd / pb_rowdot"), ("colstats_kernel", "pb_colstats")]
 
 
