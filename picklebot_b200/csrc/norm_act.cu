@@ -515,6 +515,54 @@ bn_act_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ z, const float* __restr
     }
 }
 
+// batch statistics (sums of z and z^2) through the same ring
+__global__ void __launch_bounds__(BNB_THREADS, 2)
+colstats_bulk_kernel(const __nv_bfloat16* __restrict__ z, double* __restrict__ sums, const BnBulk p) {
+    extern __shared__ uint8_t bnb_smem[];
+    __shared__ BnbCtx cx;
+    pdl_trigger();
+    const uint32_t raw = tc::smem_u32(bnb_smem);
+    const uint32_t ring = (raw + 127u) & ~127u;
+    float* sm_fold = reinterpret_cast<float*>(bnb_smem + (ring - raw));
+    bnb_init(cx);
+    pdl_wait();
+    if (threadIdx.x >= BNB_CONSUMERS) {
+        if (threadIdx.x == BNB_CONSUMERS) bnb_produce(cx, p, ring, z, nullptr);
+        return;
+    }
+    const BnbLayout L(p.C);
+    const int lane = threadIdx.x & 31;
+    float s[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s[i] = 0.f;
+    int st = 0; uint32_t ph = 0;
+    for (unsigned n = blockIdx.x; n < p.nchunks; n += gridDim.x) {
+        tc::mbar_wait_parked(&cx.full[st], ph);
+        const int rows = (int)min((unsigned)p.rc, p.M - n * (unsigned)p.rc);
+        const uint32_t zb = ring + (uint32_t)st * p.stage_pitch + (uint32_t)L.c0 * 2u;
+        if (L.active) {
+            for (int r = L.rr; r < rows; r += L.RPI) {
+                const F8 v = lds8_bf16(zb + (uint32_t)r * (uint32_t)p.C * 2u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s[i] += v.v[i]; s[8 + i] = fmaf(v.v[i], v.v[i], s[8 + i]); }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&cx.empty[st]);
+        if (++st == p.stages) { st = 0; ph ^= 1u; }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    bnb_fold_rows<16>(s, L.G, L.RPI, L.rr, sm_fold);
+    if (L.active && L.rr == 0) {
+        double* dst = sums + (size_t)(blockIdx.x % PB_STAT_REPLICAS) * 2 * p.C;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            atomicAdd(&dst[L.c0 + i], (double)s[i]);
+            atomicAdd(&dst[p.C + L.c0 + i], (double)s[8 + i]);
+        }
+    }
+}
+
 // plan: ~8 KB of rows per tensor and stage; false = use the register kernels (tiny or misaligned problems)
 static inline bool bnb_plan(long long M, long long R, int C, int tensors, const void* p0, const void* p1, BnBulk* b,
                             int* grid, size_t* smem, bool fold_scratch) {
@@ -596,6 +644,16 @@ extern "C" int pb_colstats(const void* x, int dtype, long long M, int C, double*
     cudaStream_t st = (cudaStream_t)stream;
     PB_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * PB_STAT_REPLICAS * 2 * C, st));
     PB_REQUIRE(M < (1LL << 31), "colstats: too many rows");
+    {
+        BnBulk bb; int bgrid = 0; size_t bsmem = 0;
+        if (dtype == PB_BF16 && bnb_plan(M, M, C, 1, x, nullptr, &bb, &bgrid, &bsmem, true)) {
+            static unsigned long long done = 0;
+            PB_CUDA(ensure_dyn_smem(colstats_bulk_kernel, 112 * 1024, &done));
+            PB_CUDA(launch_pdl(colstats_bulk_kernel, dim3(bgrid), dim3(BNB_THREADS), bsmem, st, (const __nv_bfloat16*)x, sums, bb));
+            PB_CHECK_LAUNCH("colstats_bulk");
+            return PB_OK;
+        }
+    }
     const int grid = row_grid(M, C);
     PB_DISPATCH_DTYPE(dtype, {
         (void)launch_pdl(colstats_kernel<T>, dim3(grid), dim3(256), 0, st, (const T*)x, sums, (unsigned)M, C);
