@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+for i in 1 2 3; do timeout 1500 python -m pytest tests -m gpu -q --tb=line -rf 2>&1 | tail -4 | cut -c1-200; done
