@@ -496,6 +496,22 @@ extern "C" int pb_pw_gemm_tc_act(const void* A, const void* W_bf16, int Bw, cons
         p.mt = std::min(4, 256 / p.block_n);
         p.mt = (int)std::max<long long>(1, std::min<long long>(p.mt, (R + BM - 1) / BM));
         while (p.mt > 1 && RING_BYTES / ((p.mt * BM + p.block_n) * BK * 2) < 3) --p.mt;   // keep >= 3 stages
+        // wave quantisation: 458 three-high tiles on 148 CTAs are 4 rounds of 3 (12 units) where 686 two-high tiles
+        // are 5 rounds of 2 (10 units) -- the 14x14 layers (100-230 k rows) sit exactly there.  Cost model: rounds x
+        // (sub-tiles + a fixed per-tile handshake worth ~0.35 sub-tiles).
+        int dev0 = 0, sms0 = 148;
+        cudaGetDevice(&dev0);
+        cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+        const long long sub_tiles = (R + BM - 1) / BM;
+        double best_cost = 1e30;
+        int best_mt = p.mt;
+        for (int m = p.mt; m >= 1; --m) {
+            const long long tiles = (long long)Bt * ((sub_tiles + m - 1) / m);
+            const long long rounds = (tiles + sms0 - 1) / sms0;
+            const double cost = (double)rounds * (m + 0.35);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best_mt = m; }
+        }
+        if (!getenv("PB_GEMM_NO_WAVE_FIT")) p.mt = best_mt;
     }
     p.m_tiles = ceil_div(R, (long long)BM * p.mt);
     p.total_tiles = (long long)Bt * p.m_tiles * p.n_tiles;
