@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q --tb=short -rf -x -k "dwconv" 2>&1 | tail -3 | cut -c1-200
+timeout 900 python -m pytest tests/test_models_gpu.py tests/test_blocks_bf16_gpu.py -m gpu -q --tb=short -rf -x 2>&1 | tail -2 | cut -c1-200
+PB_BENCH_DETAIL=gpurun_out/detail_r3l.txt timeout 900 python bench.py --steps 4 --warmup 3 --no-torch-b200 --no-cpu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); k=d['kernels']; print('cfg3:', d['value'], d['ms_per_step'], d['roofline']['frac'], 'fwd_pool', k['pb_dwconv3d_fwd_pool']['ms_per_step'], k['pb_dwconv3d_fwd_pool']['GBps'])"
+timeout 900 python bench.py --config 2 --steps 4 --warmup 3 --no-torch-b200 --no-cpu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('cfg2:', d['value'], d['ms_per_step'])"
