@@ -51,7 +51,9 @@ def test_gemm_tc_per_sample_weights(case):
 
 
 @pytest.mark.parametrize("case", [(2, 931, 160, 960), (3, 3528, 112, 672), (64, 49, 96, 576), (5, 300, 40, 120),
-                                  (2, 1000, 40, 72), (1, 50, 24, 64), (400, 130, 80, 480)])
+                                  (2, 1000, 40, 72), (1, 50, 24, 64), (400, 130, 80, 480),
+                                  # per-sample weights RESIDENT per (sample, column tile), swapped several times per CTA
+                                  (8, 2000, 40, 120), (70, 700, 112, 480), (64, 931, 160, 960), (9, 5000, 24, 72)])
 def test_gemm_tc_se_input_gradient(case, monkeypatch):
     """dy2 = (dz W) * gate + dmean of a squeeze-excite block (blocks.se_pw2_backward): the gate folded into the rows
     of per-sample transposed weights (pb_fold_gate_t_bf16), dmean pre-loaded into the TMEM accumulator by the
