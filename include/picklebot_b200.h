@@ -145,6 +145,9 @@ int pb_fold_gate_bf16(const float* W, const float* gate, void* dst, int Bt, int 
  * eval-mode BatchNorm scale of the layer's output channels) are each optional (NULL); without a gate Bt must be 1. */
 int pb_fold_scaled_bf16(const float* W, const float* gate, const float* rowscale, void* dst, int Bt, int N, int K,
                         pb_stream_t stream);
+/* the same from a weight that is already transposed: dst[b][r][c] = bf16(Wt[r][c] * gate[b][r]), Wt fp32 [R][C] (e.g. the
+ * cached pb_cast_matrix(..., PB_F32, transpose=1) of W2), gate fp32 [Bt][R], C % 8 == 0: all accesses coalesced. */
+int pb_fold_rows_bf16(const float* Wt, const float* gate, void* dst, int Bt, int R, int C, pb_stream_t stream);
 int pb_fold_gate_t_bf16(const float* W, const float* gate, void* dst, int Bt, int N, int K, pb_stream_t stream);
 /* dst bf16 [F*N][F*K] = diag(W, ..., W) for W bf16 [N][K]: the weight of a row-folded GEMM.  A layer with
  * K <= 32 input channels is run as X'[rows/F][F*K] x dst^T = C'[rows/F][F*N], which is C[rows][N] in memory,

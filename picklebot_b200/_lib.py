@@ -35,6 +35,7 @@ SIGNATURES = {
     "pb_cast_matrix": "ppiiiip",
     "pb_fold_gate_bf16": "pppiiip",
     "pb_fold_gate_t_bf16": "pppiiip",
+    "pb_fold_rows_bf16": "pppiiip",
     "pb_fold_scaled_bf16": "ppppiiip",
     "pb_block_diag_bf16": "ppiiip",
     "pb_colstats": "pilipp",

@@ -174,7 +174,8 @@ def se_pw2_backward(dz: torch.Tensor, y2: torch.Tensor, w2: torch.Tensor, cache:
         # dy2 = (dz W2) * gate + dmean: the gate goes into per-sample weights (rows of W2^T scaled), dmean pre-loads
         # the accumulator, so the GEMM runs its plain bf16 epilogue (the fp32 epilogue-vector path is write-starved:
         # 2.0 TB/s of stores against 3.7 for the plain one on the 112 -> 672 layer)
-        Wtg = ops.fold_gate_t(W.contiguous(), gate)
+        Wt32 = cache.get(("w2", "f32_t"), w2, lambda: ops.cast_matrix(W, Cout, Cexp, torch.float32, transpose=True))
+        Wtg = ops.fold_rows(Wt32, gate)
         dy2 = gemm_tc.gemm(dz, Wtg, Cexp, Cout, Bw=B, Bt=B, coladd=dmean)
     else:
         dW2, _ = ops.wgrad_simt(y2.view(-1, Cexp), dz, Cexp, Cout, ascale=gate, Bt=B)

@@ -215,6 +215,29 @@ __global__ void fold_scaled_kernel(const float* __restrict__ W, const float* __r
     *reinterpret_cast<uint4*>(dst + idx * 8) = o;
 }
 
+// Row-scaled fold from an already TRANSPOSED fp32 weight: dst[b][r][c] = Wt[r][c] * gate[b][r]  (Wt fp32 [R][C]).
+// Same result as fold_gate_t_kernel, but every access is a coalesced 16/32-byte vector (the strided gather of the
+// transposing kernel took 16 us per launch on the 112 x 672 layer).
+__global__ void fold_rows_kernel(const float* __restrict__ Wt, const float* __restrict__ gate,
+                                 __nv_bfloat16* __restrict__ dst, int R, int C, long long total8) {
+    pdl_trigger();
+    pdl_wait();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total8) return;
+    const int C8 = C >> 3;
+    const int c = (int)(idx % C8) << 3;
+    const long long q = idx / C8;
+    const int r = (int)(q % R);
+    const int b = (int)(q / R);
+    const float4* wp = reinterpret_cast<const float4*>(Wt + (long long)r * C + c);
+    const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+    const float g = __ldg(gate + (long long)b * R + r);
+    uint4 o;
+    o.x = pack_bf16x2(w0.x * g, w0.y * g); o.y = pack_bf16x2(w0.z * g, w0.w * g);
+    o.z = pack_bf16x2(w1.x * g, w1.y * g); o.w = pack_bf16x2(w1.z * g, w1.w * g);
+    *reinterpret_cast<uint4*>(dst + idx * 8) = o;
+}
+
 // Transposed twin for the input-gradient GEMM of a squeeze-excite block: dst[b][k][n] = W[n][k] * gate[b][k]
 // (W fp32 [N][K] as stored by the layer, dst bf16 [B][K][N]): the gate scales the ROWS of the transposed weight,
 // i.e. the output columns of  dy2 = dz W  -- folded here so that GEMM needs no per-column epilogue vector.
@@ -335,6 +358,16 @@ extern "C" int pb_fold_scaled_bf16(const float* W, const float* gate, const floa
     (void)launch_pdl(fold_scaled_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, W, gate, rowscale,
                      (__nv_bfloat16*)dst, N, K, n);
     PB_CHECK_LAUNCH("fold_scaled_kernel");
+    return PB_OK;
+}
+
+extern "C" int pb_fold_rows_bf16(const float* Wt, const float* gate, void* dst, int Bt, int R, int C, pb_stream_t stream) {
+    PB_REQUIRE(Wt && gate && dst && Bt > 0 && R > 0 && C > 0 && C % 8 == 0, "fold_rows: bad args (C must be a multiple of 8)");
+    PB_REQUIRE(((reinterpret_cast<uintptr_t>(Wt) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "fold_rows: pointers must be 16-byte aligned");
+    long long n = (long long)Bt * R * (C / 8);
+    (void)launch_pdl(fold_rows_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, Wt, gate,
+                     (__nv_bfloat16*)dst, R, C, n);
+    PB_CHECK_LAUNCH("fold_rows_kernel");
     return PB_OK;
 }
 

@@ -125,6 +125,17 @@ def fold_scaled(W: torch.Tensor, gate: Optional[torch.Tensor], rowscale: Optiona
     return dst
 
 
+def fold_rows(Wt: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
+    """bf16 [B][R][C] = Wt[r][c] * gate[b][r] for an fp32 weight that is already transposed ([R][C]): what ``fold_gate_t``
+    computes from the untransposed weight, with coalesced accesses only."""
+    _f32(Wt, "fold_rows.Wt"); _f32(gate, "fold_rows.gate")
+    R, C = Wt.shape[0], Wt.shape[1]
+    B = gate.shape[0]
+    dst = torch.empty((B, R, C), dtype=torch.bfloat16, device=Wt.device)
+    call("pb_fold_rows_bf16", Wt.data_ptr(), gate.data_ptr(), dst.data_ptr(), B, R, C, _st())
+    return dst
+
+
 def fold_gate_t(W: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
     """bf16 [B][K][N] = W[n][k] * gate[b][k]: the per-sample weights of the input-gradient GEMM  dy2 = (dz W) * gate."""
     _f32(W, "fold_gate_t.W"); _f32(gate, "fold_gate_t.gate")

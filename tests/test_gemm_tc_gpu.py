@@ -66,6 +66,7 @@ def test_gemm_tc_se_input_gradient(case, monkeypatch):
     gate = rnd(Bt, Cexp, seed=3).abs() + 0.1
     dmean = rnd(Bt, Cexp, seed=4, scale=2.0)
     Wtg = ops.fold_gate_t(W, gate)
+    assert torch.equal(ops.fold_rows(W.t().contiguous(), gate), Wtg)      # the coalesced variant blocks.py uses
     assert Wtg.shape == (Bt, Cexp, Cout)
     assert rel_err(Wtg.float(), W.t()[None] * gate[:, :, None]) < 4e-3
     dy2 = gemm_tc.gemm(dz, Wtg, Cexp, Cout, Bw=Bt, Bt=Bt, coladd=dmean)
