@@ -422,6 +422,11 @@ bn_bwd_bulk_kernel(const void* __restrict__ dout, const __nv_bfloat16* __restric
         if (MODE == 1) { load_vec8(coef + L.c0, k0); load_vec8(coef + p.C + L.c0, k1); }
     }
     int st = 0; uint32_t ph = 0;
+    unsigned b_lo = 1, b_hi = 0;                 // rows of the sample whose vectors are cached (empty range at first)
+    F8 dvb;
+    float mkv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dvb.v[i] = 0.f; mkv[i] = 1.f; }
     for (unsigned n = blockIdx.x; n < p.nchunks; n += gridDim.x) {
         tc::mbar_wait_parked(&cx.full[st], ph);
         const unsigned row0 = n * (unsigned)p.rc;
@@ -432,12 +437,21 @@ bn_bwd_bulk_kernel(const void* __restrict__ dout, const __nv_bfloat16* __restric
                 const unsigned m = row0 + (unsigned)r;
                 const uint32_t off = (uint32_t)r * (uint32_t)p.C * 2u;
                 const F8 zv = lds8_bf16(zb + off);
-                const unsigned b = (BCAST || mask) ? m / p.R : 0;
+                if ((BCAST || mask) && (m < b_lo || m >= b_hi)) {      // per-sample vectors: reload when the sample changes,
+                    const unsigned b = m / p.R;                        // not per row (a division and 2-4 loads each)
+                    b_lo = b * p.R; b_hi = b_lo + p.R;
+                    if (BCAST) dvb = load8(reinterpret_cast<const float*>(dout) + (size_t)b * p.C + L.c0);
+                    if (mask) load_vec8(mask + (size_t)b * p.C + L.c0, mkv);
+                }
                 F8 dv;
-                if (BCAST) dv = load8(reinterpret_cast<const float*>(dout) + (size_t)b * p.C + L.c0);
+                if (BCAST) dv = dvb;
                 else       dv = lds8_bf16(zb + p.tensor_pitch + off);
                 float du[8], xh[8];
-                bn_bwd_math<ACT>(zv, dv, mask ? mask + (size_t)b * p.C + L.c0 : nullptr, sc, sh, a, bb, slope, du, xh);
+                bn_bwd_math<ACT>(zv, dv, nullptr, sc, sh, a, bb, slope, du, xh);
+                if (mask) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) du[i] *= mkv[i];
+                }
                 if (MODE == 0) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { s[i] += du[i]; s[8 + i] = fmaf(du[i], xh[i], s[8 + i]); }
@@ -488,6 +502,10 @@ bn_act_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ z, const float* __restr
     const int lane = threadIdx.x & 31;
     float sc[8], sh[8];
     if (L.active) { load_vec8(scale + L.c0, sc); load_vec8(shift + L.c0, sh); }
+    unsigned b_lo = 1, b_hi = 0;
+    float mkv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mkv[i] = 1.f;
     int st = 0; uint32_t ph = 0;
     for (unsigned n = blockIdx.x; n < p.nchunks; n += gridDim.x) {
         tc::mbar_wait_parked(&cx.full[st], ph);
@@ -501,10 +519,13 @@ bn_act_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ z, const float* __restr
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v.v[i] = actf<ACT>(fmaf(v.v[i], sc[i], sh[i]), slope);
                 if (mask) {
-                    float mk[8];
-                    load_vec8(mask + (size_t)(m / p.R) * p.C + L.c0, mk);
+                    if (m < b_lo || m >= b_hi) {                       // reload the sample's mask when the sample changes
+                        const unsigned b = m / p.R;
+                        b_lo = b * p.R; b_hi = b_lo + p.R;
+                        load_vec8(mask + (size_t)b * p.C + L.c0, mkv);
+                    }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v.v[i] *= mk[i];
+                    for (int i = 0; i < 8; ++i) v.v[i] *= mkv[i];
                 }
                 store8(out + (size_t)m * p.C + L.c0, v);
             }
