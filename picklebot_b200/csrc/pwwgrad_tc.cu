@@ -52,7 +52,10 @@ static int pick_box_width(int W) {
     int best = 64, best_cost = 1 << 30;
     for (int ew : {64, 32, 16}) {
         const int boxes = ceil_div(W, ew);
-        const int cost = boxes * ew + 4 * boxes;
+        // a 32-byte box row still costs a 64-byte transfer from L2 (ncu: 424 MB moved for 231 MB on 24 -> 72 channels
+        // with 16-wide boxes), so boxes narrower than 32 channels are charged as 32
+        static const bool old_cost = getenv("PB_WGRAD_OLD_BOXCOST") != nullptr;
+        const int cost = boxes * (old_cost ? ew : std::max(ew, 32)) + 4 * boxes;
         if (cost < best_cost) { best_cost = cost; best = ew; }
     }
     return best;
@@ -67,6 +70,10 @@ static int pick_fold(long long R, int K, int N) {
     if (std::min(K, N) > 32) return 1;
     for (int F : {4, 2})
         if (R % F == 0 && K * F <= 128 && N * F <= 128) return F;
+    // 24 <-> 72 channels: unfolded, the 48-byte rows of one operand and the 32-byte boxes of the other make TMA move
+    // 424 MB for 231 MB of activations (ncu: the L2 -> SM fabric is the limit at 7 TB/s); folded by two the rows are
+    // 96 / 288 bytes in 128-byte boxes (1.33x), at the price of a second 128-row output tile
+    if (R % 2 == 0 && K * 2 <= 256 && N * 2 <= 256 && !getenv("PB_WGRAD_NO_WIDE_FOLD")) return 2;
     return 1;
 }
 
@@ -264,21 +271,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__
                     }
                 }
             } else {
-                // folded: one tile; TMEM lane (i, n) keeps the columns of diagonal block i -> partial slice i
-                const int np = q * 32 + lane;
-                const int i = np / p.N, n = np - i * p.N;
-                const bool live = i < pl.fold;
-                float* dst = p.partial + ((slice * pl.fold + i) * p.N + n) * p.K;
-                const int lo = i * p.K, hi = lo + p.K;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-                for (int c0 = 0; c0 < pl.KW; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(taddr + (uint32_t)c0, r);
-                    tmem_ld_wait();
+                // folded: TMEM lane (i, n) of tile j (folded row j*128 + lane) keeps the columns of diagonal block i
+                // -> partial slice i
+                for (int j = 0; j < ntiles; ++j) {
+                    const int np = (nt0 + j) * 128 + q * 32 + lane;
+                    const int i = np / p.N, n = np - i * p.N;
+                    const bool live = i < pl.fold;
+                    float* dst = p.partial + ((slice * pl.fold + i) * p.N + n) * p.K;
+                    const int lo = i * p.K, hi = lo + p.K;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * pl.KW);
+                    for (int c0 = 0; c0 < pl.KW; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(taddr + (uint32_t)c0, r);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const int col = c0 + e;
-                        if (live && col >= lo && col < hi) dst[col - lo] = __uint_as_float(r[e]);
+                        for (int e = 0; e < 16; ++e) {
+                            const int col = c0 + e;
+                            if (live && col >= lo && col < hi) dst[col - lo] = __uint_as_float(r[e]);
+                        }
                     }
                 }
             }
