@@ -1,4 +1,4 @@
-"""The bench.py JSON contract, checked on the committed evidence (profiles/r01_bench_*.json): every key the
+"""The bench.py JSON contract, checked on the committed evidence (profiles/r0*_bench_*.json): every key the
 driver reads is present and self-consistent.  Runs on CPU; the numbers themselves come from B200 runs."""
 import glob
 import json
@@ -7,7 +7,8 @@ import os
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FILES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_n*.json")))
+FILES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_bench_n*.json")) +
+               glob.glob(os.path.join(ROOT, "profiles", "r02_bench_config*.json")))
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
@@ -32,7 +33,22 @@ def test_bench_line_has_the_contract_keys(path):
         assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
-def test_reference_arm_line():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_reference_arm.json")))
+@pytest.mark.parametrize("name", ["r01_bench_reference_arm.json", "r02_bench_reference_arm.json"])
+def test_reference_arm_line(name):
+    d = json.load(open(os.path.join(ROOT, "profiles", name)))
     assert d["impl"] == "reference" and d["unit"] == "clips/s" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_round2_line_carries_the_same_gpu_torch_baseline_and_traffic():
+    """Round 2: the default line times the reference's own ops on the same B200 and reads the dominant kernel's DRAM
+    traffic from the committed ncu launch list (profiles/roofline_traffic.json, tools/roofline_traffic.py)."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")))
+    t = d["torch_b200"]
+    assert t["eager"]["value"] > 0 and t["compiled"]["value"] > 0 and t["eager"]["micro_batch"] == 64
+    assert d["value"] > 10 * t["compiled"]["value"]
+    r = d["roofline"]
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    assert r["kernel"] in traffic and traffic[r["kernel"]]["dram_bytes_per_launch"] > 0
+    assert 0.5 < r["traffic"] / r["alg_bytes_per_launch"] <= 1.05       # no re-reads beyond the algorithmic bytes
+    assert r["frac"] <= r["frac_of_rw_bound"] <= 1.0
